@@ -1,0 +1,109 @@
+"""Deterministic test inputs (test infrastructure).  Every dataset is written as a reference read
+library (<prefix>.bin + <prefix>.lib_info); golden.json records the md5 of each .bin so a drifted RNG
+stream fails loudly instead of silently changing the inputs."""
+import hashlib
+import os
+import random
+
+import numpy as np
+
+from megagta_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN_DIR = os.path.join(HERE, "golden")
+CODE = {c: i for i, c in enumerate("ACGT")}
+
+
+def _smoke(prefix):
+    """SURVEY.md Appendix E.2 (CPython `random`, seed 1): 20k x 100 bp from one 20 kb genome."""
+    random.seed(1)
+    G = "".join(random.choice("ACGT") for _ in range(20000))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    reads = np.empty((20000, 100), dtype=np.uint8)
+    for i in range(20000):
+        p = random.randrange(0, len(G) - 100)
+        s = G[p:p + 100]
+        if random.random() < 0.5:
+            s = "".join(comp[c] for c in reversed(s))
+        s = list(s)
+        for j in range(100):
+            if random.random() < 0.01:
+                s[j] = random.choice("ACGT")
+        reads[i] = [CODE[c] for c in s]
+    synth.write_read_lib(prefix, [reads], 100, 20000)
+
+
+def _adversarial(prefix):
+    """Variable-length reads with palindromes, homopolymers, dinucleotide repeats, reads shorter than
+    k+1, very high coverage (multiplicity > 254 and > 65535 items in one group) and empty-ish reads."""
+    rng = np.random.default_rng(7)
+    g = rng.integers(0, 4, size=3000, dtype=np.uint8)
+    pal_half = rng.integers(0, 4, size=40, dtype=np.uint8)
+    pal = np.concatenate([pal_half, 3 - pal_half[::-1]])          # reverse-complement palindrome, 80 bp
+    g[1000:1080] = pal
+    reads = []
+    for i in range(30000):                                         # ~1000x coverage of a 3 kb genome
+        L = int(rng.integers(20, 121))
+        p = int(rng.integers(0, len(g) - L))
+        r = g[p:p + L].copy()
+        if rng.random() < 0.5:
+            r = 3 - r[::-1]
+        e = rng.random(L) < 0.005
+        r[e] = (r[e] + rng.integers(1, 4, size=int(e.sum()), dtype=np.uint8)) % 4
+        reads.append(r)
+    for i in range(900):                                           # poly-A / poly-T: one giant group
+        reads.append(np.full(int(rng.integers(90, 121)), 0 if i % 3 else 3, dtype=np.uint8))
+    for i in range(300):                                           # (AC)n and (ACG)n repeats
+        L = int(rng.integers(60, 121))
+        unit = [0, 1] if i % 2 else [0, 1, 2]
+        reads.append(np.array((unit * L)[:L], dtype=np.uint8))
+    for i in range(50):                                            # exact palindromic reads
+        reads.append(pal.copy())
+    for L in (1, 5, 16, 17, 31, 32, 33):                           # shorter than any k+1 we test
+        reads.append(rng.integers(0, 4, size=L, dtype=np.uint8))
+    order = rng.permutation(len(reads))
+    synth.write_variable_reads(prefix, [reads[i] for i in order])
+
+
+def _meta(n, L):
+    def f(prefix):
+        synth.write_metagenome(prefix, n, L, seed=20261017, n_genomes=16, glen=(20_000, 200_000))
+    return f
+
+
+def _tiny(prefix):
+    rng = np.random.default_rng(3)
+    g = rng.integers(0, 4, size=400, dtype=np.uint8)
+    reads = [g[p:p + 60].copy() for p in rng.integers(0, 340, size=200)]
+    synth.write_variable_reads(prefix, reads)
+
+
+DATASETS = {
+    "tiny": _tiny,                 # 200 x 60 bp
+    "smoke": _smoke,               # 20k x 100 bp
+    "adversarial": _adversarial,   # ~31k variable-length reads
+    "meta200k": _meta(200_000, 100),
+    "meta1m": _meta(1_000_000, 100),   # BASELINE config 0 shape (1M x 100 bp), GPU tests only
+}
+
+
+def md5(path):
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def materialise(name, directory):
+    """Write dataset `name` under `directory` (cached) and return its read-library prefix."""
+    os.makedirs(directory, exist_ok=True)
+    prefix = os.path.join(directory, name)
+    if not (os.path.exists(prefix + ".bin") and os.path.exists(prefix + ".lib_info")):
+        if name == "xander":
+            import shutil
+            shutil.copy(os.path.join(GOLDEN_DIR, "xander.bin"), prefix + ".bin")
+            shutil.copy(os.path.join(GOLDEN_DIR, "xander.lib_info"), prefix + ".lib_info")
+        else:
+            DATASETS[name](prefix)
+    return prefix
