@@ -1,0 +1,138 @@
+/*
+ * mgta_cuda.h -- C ABI of libmgta_cuda.so: the B200 (sm_100a) implementation of MegaGTA's CX1
+ * reads -> succinct de Bruijn graph construction (`megagta buildgraph`).
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this path: it is one process whose
+ * `build_graph()` (reference src/build_graph.cpp:33-135, declared src/megagta.cpp:9) installs 12
+ * CX1 callbacks twice (stage 1: build_graph.cpp:100-113, stage 2: :120-132) and calls
+ * `CX1::run()` (src/cx1.h:443-623).  The only historic GPU seam is the undeclared
+ * `lv2_gpu_sort(...)` / `alloc_gpu_buffers` / `free_gpu_buffers` under `#ifdef USE_GPU`
+ * (src/cx1_read2sdbg_s1.cpp:308,619,945; src/cx1_read2sdbg_s2.cpp:391,697,926).  A host
+ * `build_graph()` replacement (megagta_b200/csrc/host/build_graph_b200.cpp) keeps the reference's
+ * option table, read-library loader and output writer and calls the entry points below; see
+ * INTEGRATION.md for the patch a reference maintainer would apply.
+ *
+ * Conventions: plain C, POD arguments, no exceptions cross the boundary.  Every function returns
+ * 0 on success and a negative mgta_status on failure; mgta_last_error() gives the message.
+ * One caller thread per context.  The caller owns all host buffers; the library owns all device
+ * memory.  There is NO CPU fallback: without a CUDA device mgta_ctx_create() fails.
+ */
+#ifndef MGTA_CUDA_H_
+#define MGTA_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGTA_NUM_BUCKETS 65536 /* reference cx1_read2sdbg.h:66 (kNumBuckets = 4^8) */
+#define MGTA_MAX_K 127         /* reference definitions.h:56 (kMaxK) */
+
+typedef enum {
+    MGTA_OK = 0,
+    MGTA_ERR_ARG = -1,      /* bad argument / option (k range, missing reads, ...) */
+    MGTA_ERR_CUDA = -2,     /* CUDA runtime error, incl. "no device" */
+    MGTA_ERR_MEM = -3,      /* HBM budget too small for the largest bucket */
+    MGTA_ERR_STATE = -4,    /* call order (stage 2 before reads, ...) */
+    MGTA_ERR_INTERNAL = -5  /* device-side consistency check failed */
+} mgta_status;
+
+typedef struct mgta_ctx mgta_ctx;
+
+/* Options of one context = one GPU = one contiguous lv1-bucket shard.
+ * Replaces read2sdbg_opt_t / read2sdbg_global_t fields (reference cx1_read2sdbg.h:36-59,76-89). */
+typedef struct {
+    int32_t kmer_k;           /* -k: graph order; edges are (k+1)-mers.  9 <= k <= 127 */
+    int32_t min_count;        /* -m: solid (k+1)-mer threshold; 1 skips stage 1 */
+    int32_t need_mercy;       /* --need_mercy: also emit mercy candidates in stage 1 */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t rank;             /* shard index in [0, world) */
+    int32_t world;            /* number of bucket shards (GPUs); 1 = whole graph */
+    int64_t hbm_budget_bytes; /* --gpu_mem: 0 = 90 % of the currently free device memory */
+    void *stream;             /* cudaStream_t to launch on; NULL = a stream owned by the context */
+    int32_t sort_items_cap;   /* items per on-chip sort tile (test hook); 0 = auto */
+    int32_t reserved;
+} mgta_opts;
+
+/* One delivery of stage-2 output: the records of buckets [bucket_begin, bucket_end), concatenated
+ * in ascending bucket order (the layout SdbgWriter::write produces per bucket,
+ * sdbg_multi_io.h:83-112).  `meta` holds 3 int64 per bucket of the range: num_items, num_tips,
+ * num_large_mul (the sdbg_info row, sdbg_multi_io.h:178-185).  Pointers are valid only during the
+ * call.  Deliveries arrive in ascending bucket order. */
+typedef int (*mgta_bucket_sink)(void *user, int32_t bucket_begin, int32_t bucket_end,
+                                const void *bytes, uint64_t n_bytes, const int64_t *meta);
+
+/* Per-stage statistics (device-timed with CUDA events on the context's stream). */
+typedef struct {
+    uint64_t n_items;        /* items sorted (stage-1 (k-1)-mer contexts / stage-2 edge contexts) */
+    uint64_t n_batches;      /* bucket-range batches the HBM budget forced */
+    uint64_t n_launches;     /* kernels launched */
+    uint64_t n_giants;       /* groups too large for the on-chip sort (counted, not sorted) */
+    uint64_t out_bytes;      /* stage 2: bytes of SdBG records emitted by this shard */
+    uint64_t n_edges;        /* stage 2: records emitted by this shard (total_size share) */
+    float ms_total;          /* whole stage, device time */
+    float ms_hist;           /* lv1 bucket histogram kernel */
+    float ms_extract;        /* item extraction + bucket scatter */
+    float ms_partition;      /* MSD digit partition levels */
+    float ms_sort_emit;      /* on-chip multi-word LSD radix sort + counting / emission */
+    int32_t key_words;       /* u32 words per key */
+    int32_t item_words;      /* u32 words per item (key + payload) */
+    int32_t sort_cap;        /* items per on-chip sort tile */
+    int32_t msd_levels;      /* digit partition levels that ran */
+} mgta_stage_stats;
+
+int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out);
+void mgta_ctx_destroy(mgta_ctx *ctx);
+const char *mgta_last_error(const mgta_ctx *ctx); /* ctx may be NULL: last create error */
+
+/* Reads as the reference holds them after ReadBinaryLibs(..., is_reverse=true)
+ * (read_lib_functions-inl.h:233-261; sequence_package.h:34-406): 2-bit bases, MSB first, 16 per
+ * u32, bit-contiguous, each read REVERSED; start_idx[i] = first base of read i, start_idx[n_reads]
+ * = total bases.  Reads [n_short_reads, n_reads) are assist sequences (always solid, s2.cpp:276).
+ * max_read_len = longest short read (s1.cpp:119).  Copies host -> device. */
+int mgta_set_reads(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_t n_words, const uint64_t *start_idx,
+                   uint64_t n_reads, uint64_t n_short_reads, int32_t max_read_len);
+
+/* lv1 bucket histograms (reference s1_lv0_calc_bucket_size s1.cpp:177-229 and
+ * s2_lv0_calc_bucket_size s2.cpp:252-315).  hist: int64[65536], whole bucket space. */
+int mgta_stage1_histogram(mgta_ctx *ctx, int64_t *hist);
+int mgta_stage2_histogram(mgta_ctx *ctx, int64_t *hist);
+
+/* Stage 1 (reference cx1.run() with the s1 callbacks): marks solid (k+1)-mers of this shard's
+ * buckets in the device-resident is_solid vector and accumulates edge_counting
+ * (int64[65536], may be NULL; s1.cpp:744-746).  No-op success when min_count == 1. */
+int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting);
+
+/* Exchange step between the stages when world > 1: the device bit vector (one bit per base
+ * position, bit start_idx[r]+o <=> edge offset o of read r).  Each bit is set by exactly one shard,
+ * so an all-reduce SUM over uint32 words (NCCL) merges the shards.  */
+int mgta_solid_device_buffer(mgta_ctx *ctx, void **dev_ptr, uint64_t *n_bytes);
+
+/* is_solid in the reference's layout (AtomicBitVector, atomic_bit_vector.h:58-60; bit index
+ * (max_read_len-k)*read_id + offset, s1.cpp:151,760).  n_bytes >= ceil(n_short*(max_len-k)/8). */
+int mgta_get_is_solid(mgta_ctx *ctx, uint8_t *host, uint64_t n_bytes);
+int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_bytes);
+
+/* Mercy candidates of this shard (s1.cpp:762-826): packed ((start_idx+kmer_offset)<<2)|flag.
+ * Valid after mgta_stage1 with need_mercy.  *n receives the count; copies min(*n, cap). */
+int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t cap, uint64_t *n);
+
+/* Stage 2 (cx1.run() with the s2 callbacks + SdbgWriter): emits this shard's buckets in ascending
+ * order.  sink may be NULL (device-resident run: records are produced and counted, not copied).
+ * totals: int64[10] = num_w[0..8], num_last1 (sdbg_multi_io.h:114-143); may be NULL. */
+int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals);
+
+/* First/last+1 bucket of this shard for the stage whose histogram was computed last. */
+int mgta_shard_range(mgta_ctx *ctx, int32_t *bucket_begin, int32_t *bucket_end);
+
+int mgta_get_stats(mgta_ctx *ctx, int stage /*1|2*/, mgta_stage_stats *out);
+
+/* u32 words per sort key: ceil((2(k-1)+6)/32) stage 1 (s1.cpp:246), ceil((2k+4)/32) stage 2 (s2.cpp:331) */
+int mgta_words_per_key(int stage, int kmer_k);
+int mgta_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGTA_CUDA_H_ */

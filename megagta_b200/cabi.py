@@ -1,0 +1,180 @@
+"""ctypes binding of libmgta_cuda.so (include/mgta_cuda.h).  There is no fallback: if the library is
+missing or no CUDA device is present, loading / context creation raises."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libmgta_cuda.so")
+NUM_BUCKETS = 65536
+
+
+class MgtaError(RuntimeError):
+    pass
+
+
+class Opts(ctypes.Structure):
+    _fields_ = [("kmer_k", ctypes.c_int32), ("min_count", ctypes.c_int32), ("need_mercy", ctypes.c_int32),
+                ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
+                ("hbm_budget_bytes", ctypes.c_int64), ("stream", ctypes.c_void_p),
+                ("sort_items_cap", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class StageStats(ctypes.Structure):
+    _fields_ = [("n_items", ctypes.c_uint64), ("n_batches", ctypes.c_uint64), ("n_launches", ctypes.c_uint64),
+                ("n_giants", ctypes.c_uint64), ("out_bytes", ctypes.c_uint64), ("n_edges", ctypes.c_uint64),
+                ("ms_total", ctypes.c_float), ("ms_hist", ctypes.c_float), ("ms_extract", ctypes.c_float),
+                ("ms_partition", ctypes.c_float), ("ms_sort_emit", ctypes.c_float),
+                ("key_words", ctypes.c_int32), ("item_words", ctypes.c_int32), ("sort_cap", ctypes.c_int32),
+                ("msd_levels", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                        ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64))
+
+EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_stage1_histogram",
+           "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
+           "mgta_get_mercy_candidates", "mgta_stage2", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
+           "mgta_abi_version"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MgtaError("%s not built (run `python -c 'import __graft_entry__ as g; g.build()'`)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.mgta_last_error.restype = ctypes.c_char_p
+        lib.mgta_last_error.argtypes = [ctypes.c_void_p]
+        lib.mgta_ctx_create.argtypes = [ctypes.POINTER(Opts), ctypes.POINTER(ctypes.c_void_p)]
+        lib.mgta_ctx_destroy.argtypes = [ctypes.c_void_p]
+        lib.mgta_ctx_destroy.restype = None
+        lib.mgta_set_reads.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                       ctypes.c_uint64, ctypes.c_int32]
+        lib.mgta_stage1_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_stage2_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_stage1.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_solid_device_buffer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                 ctypes.POINTER(ctypes.c_uint64)]
+        lib.mgta_get_is_solid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        lib.mgta_set_is_solid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        lib.mgta_get_mercy_candidates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                                  ctypes.POINTER(ctypes.c_uint64)]
+        lib.mgta_stage2.argtypes = [ctypes.c_void_p, SINK, ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_shard_range.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+        lib.mgta_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(StageStats)]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One GPU / one lv1-bucket shard.  Thin object wrapper over the C ABI."""
+
+    def __init__(self, k, min_count=2, need_mercy=False, device=0, rank=0, world=1, hbm_budget_bytes=0, stream=None,
+                 sort_items_cap=0):
+        self.lib = load()
+        self.opts = Opts(k, min_count, int(need_mercy), device, rank, world, hbm_budget_bytes, stream, sort_items_cap, 0)
+        self.h = ctypes.c_void_p()
+        rc = self.lib.mgta_ctx_create(ctypes.byref(self.opts), ctypes.byref(self.h))
+        if rc != 0:
+            raise MgtaError("mgta_ctx_create: %s" % self.lib.mgta_last_error(None).decode())
+        self.k, self.m = k, min_count
+        self._reads = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MgtaError("%s failed (%d): %s" % (what, rc, self.lib.mgta_last_error(self.h).decode()))
+
+    def close(self):
+        if self.h:
+            self.lib.mgta_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_reads(self, seq, start, n_short=None, max_len=None):
+        seq = np.ascontiguousarray(seq, dtype=np.uint32)
+        start = np.ascontiguousarray(start, dtype=np.uint64)
+        n = len(start) - 1
+        n_short = n if n_short is None else n_short
+        if max_len is None:
+            lens = np.diff(start[:n_short + 1].astype(np.int64))
+            max_len = int(lens.max()) if len(lens) else 0
+        self._reads = (seq, start)
+        self.n_short, self.max_len = n_short, max_len
+        self._check(self.lib.mgta_set_reads(self.h, _p(seq), len(seq), _p(start), n, n_short, max_len), "mgta_set_reads")
+
+    def histogram(self, stage):
+        h = np.zeros(NUM_BUCKETS, dtype=np.int64)
+        fn = self.lib.mgta_stage1_histogram if stage == 1 else self.lib.mgta_stage2_histogram
+        self._check(fn(self.h, _p(h)), "mgta_stage%d_histogram" % stage)
+        return h
+
+    def stage1(self):
+        ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
+        self._check(self.lib.mgta_stage1(self.h, _p(ec)), "mgta_stage1")
+        return ec
+
+    def get_is_solid(self):
+        n = (max(0, self.max_len - self.k) * self.n_short + 7) // 8
+        buf = np.zeros(n + 8, dtype=np.uint8)
+        self._check(self.lib.mgta_get_is_solid(self.h, _p(buf), len(buf)), "mgta_get_is_solid")
+        return buf
+
+    def set_is_solid(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._check(self.lib.mgta_set_is_solid(self.h, _p(buf), len(buf)), "mgta_set_is_solid")
+
+    def solid_device_buffer(self):
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self.lib.mgta_solid_device_buffer(self.h, ctypes.byref(p), ctypes.byref(n)), "mgta_solid_device_buffer")
+        return p.value, n.value
+
+    def mercy_candidates(self):
+        n = ctypes.c_uint64()
+        self._check(self.lib.mgta_get_mercy_candidates(self.h, None, 0, ctypes.byref(n)), "mgta_get_mercy_candidates")
+        out = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self.lib.mgta_get_mercy_candidates(self.h, _p(out), n.value, ctypes.byref(n)),
+                        "mgta_get_mercy_candidates")
+        return out
+
+    def stage2(self, collect=True):
+        """-> (stream bytes, meta int64[65536,3], totals int64[10]).  collect=False keeps the records on the device."""
+        parts = []
+        meta = np.zeros((NUM_BUCKETS, 3), dtype=np.int64)
+
+        def sink(user, b0, b1, ptr, nbytes, mptr):
+            if nbytes:
+                parts.append(ctypes.string_at(ptr, nbytes))
+            meta[b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
+            return 0
+
+        cb = SINK(sink) if collect else ctypes.cast(None, SINK)
+        totals = np.zeros(10, dtype=np.int64)
+        self._check(self.lib.mgta_stage2(self.h, cb, None, _p(totals)), "mgta_stage2")
+        return b"".join(parts), meta, totals
+
+    def shard_range(self):
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self.lib.mgta_shard_range(self.h, ctypes.byref(a), ctypes.byref(b)), "mgta_shard_range")
+        return a.value, b.value
+
+    def stats(self, stage):
+        s = StageStats()
+        self._check(self.lib.mgta_get_stats(self.h, stage, ctypes.byref(s)), "mgta_get_stats")
+        return s.as_dict()

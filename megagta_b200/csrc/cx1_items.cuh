@@ -1,0 +1,91 @@
+// cx1_items.cuh -- which sort items one base position of one read contributes, and their keys.
+//
+// Stage 1 (reference s1_lv0_calc_bucket_size s1.cpp:177-229, s1_lv1_fill_offset :408-513,
+// s1_extract_subtstr_ :515-596): the (k-1)-mer S at read offset p with its neighbours
+// prev,head | S | tail,next.  Read ends (p == 0, p == L-k+1) go in on BOTH strands, interior
+// positions on the smaller of (S, rc(S)), palindromes by `head <= 3 - tail` (s1.cpp:482-495).
+//   key  = S (or rc S) | zero pad | head<<3|tail in the low 6 bits of the last word (s1.cpp:575-588)
+//   value (ours, the reference's is an lv1 offset): kpos<<8 | strand<<6 | prev<<3 | next, where
+//          kpos = absolute base index of S = start_idx[read] + p (the (k+1)-mer head S tail starts at
+//          kpos-1), or S1_NO_EDGE for assist reads (never marked solid, no mercy: s1.cpp:757,785).
+//
+// Stage 2 (reference s2_lv0_calc_bucket_size s2.cpp:252-315, s2_lv1_fill_offset :475-584,
+// s2_lv2_extract_substr_ :586-677): a solid edge e = R[o..o+k] with r = rc(e) contributes
+//   solid  : (b=e[0], S=e[1..k-1], a=e[k])          and, unless e is a palindrome, the same from r
+//   left $ : (b=$,   S=e[0..k-2], a=e[k-1]) ; (b=r[1], S=r[2..k], a=$)      if o==0 or !solid(o-1)
+//   right $: (b=e[1], S=e[2..k],  a=$)      ; (b=$,   S=r[0..k-2], a=r[k-1]) if o==L-k-1 or !solid(o+1)
+//   key = S a | zero pad | (a!=$)<<3 | b in the low 4 bits of the last word (s2.cpp:639-641,668-670)
+//
+// __host__ __device__ so the CPU logic test can drive the same code against the oracle.
+#pragma once
+#include "kmer_ops.cuh"
+
+namespace mgta {
+
+constexpr int SENT = 4;                                 // kSentinelValue, cx1_read2sdbg.h:71
+constexpr uint64_t S1_NO_EDGE = (1ull << 40) - 1;       // payload marker: item never marks a solid edge
+
+MGTA_HD int comp_char(int c) { return c == SENT ? SENT : 3 - c; }
+
+MGTA_HD int key_words_s1(int k) { return (2 * (k - 1) + 6 + 31) / 32; }   // s1.cpp:246
+MGTA_HD int key_words_s2(int k) { return (2 * k + 4 + 31) / 32; }         // s2.cpp:331
+
+// words: staged read words; q: char offset of the position inside `words`; g: absolute base index
+// of the position; p: offset inside its read of length L.  Caller guarantees L >= k+1, p <= L-k+1.
+// emit(key[W], value64)
+template <int W, class Emit>
+MGTA_HD void s1_position(const uint32_t *words, uint32_t q, uint64_t g, int p, int L, int k, bool short_read,
+                         Emit &&emit) {
+    uint32_t S[W], R[W];
+    load_chars<W>(words, q, k - 1, S);
+    revcomp<W>(S, k - 1, R);
+    const int head = p > 0 ? char_at(words, q - 1) : SENT;
+    const int prev = p > 1 ? char_at(words, q - 2) : SENT;
+    const int tail = p + k - 1 < L ? char_at(words, q + k - 1) : SENT;
+    const int next = p + k < L ? char_at(words, q + k) : SENT;
+    const bool ends = (p == 0) || (p == L - k + 1);
+    const int c = ends ? 0 : cmp_words<W>(S, R);
+    const bool tie_fw = head <= 3 - tail;                               // s1.cpp:486
+    const bool fw = ends || c < 0 || (c == 0 && tie_fw);
+    const bool rv = ends || c > 0 || (c == 0 && !tie_fw);
+    const uint64_t edge = short_read ? g : S1_NO_EDGE;
+    if (fw) {
+        S[W - 1] |= (uint32_t)((head << 3) | tail);
+        emit(S, (edge << 8) | (0u << 6) | (uint64_t)((prev << 3) | next));
+    }
+    if (rv) {
+        R[W - 1] |= (uint32_t)((comp_char(tail) << 3) | comp_char(head));
+        emit(R, (edge << 8) | (1u << 6) | (uint64_t)((comp_char(next) << 3) | comp_char(prev)));
+    }
+}
+
+// Caller guarantees L >= k+1, o < L-k and solid(o).  emit(key[W])
+template <int W, class Emit>
+MGTA_HD void s2_position(const uint32_t *words, uint32_t q, int o, int L, int k, bool solid_prev, bool solid_next,
+                         Emit &&emit) {
+    uint32_t E[W], R[W];
+    load_chars<W>(words, q, k + 1, E);
+    revcomp<W>(E, k + 1, R);
+    const bool pal = cmp_words<W>(E, R) == 0;
+    const bool left = (o == 0) || !solid_prev;
+    const bool right = (o == L - k - 1) || !solid_next;
+    auto put = [&](const uint32_t(&X)[W], int c, bool has_a) {
+        uint32_t Y[W];
+        sub_chars<W>(X, c, has_a ? k : k - 1, Y);
+        const int b = c ? (int)((X[0] >> (32 - 2 * c)) & 3u) : SENT;
+        Y[W - 1] |= (uint32_t)(((has_a ? 1 : 0) << 3) | b);
+        emit(Y);
+    };
+    if (left) {
+        put(E, 0, true);
+        if (!pal) put(R, 2, false);
+    }
+    put(E, 1, true);
+    if (!pal) put(R, 1, true);
+    if (right) {
+        put(E, 2, false);
+        if (!pal) put(R, 0, true);
+    }
+}
+
+}  // namespace mgta

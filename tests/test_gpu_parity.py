@@ -1,0 +1,126 @@
+"""GPU parity tests: libmgta_cuda.so through its C ABI vs the oracle and the reference-binary goldens."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from megagta_b200 import cabi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(rd, k, m, **kw):
+    with cabi.Context(k, m, **kw) as ctx:
+        ctx.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+        res = {}
+        if m > 1:
+            res["h1"] = ctx.histogram(1)
+            res["counting"] = ctx.stage1()
+            res["is_solid"] = ctx.get_is_solid()
+            res["stats1"] = ctx.stats(1)
+        res["h2"] = ctx.histogram(2)
+        res["stream"], res["meta"], res["totals"] = ctx.stage2()
+        res["stats2"] = ctx.stats(2)
+        return res
+
+
+def check_vs_oracle(rd, k, m, got):
+    exp_solid = None
+    if m > 1:
+        exp_solid, exp_ec, _ = O.stage1(rd, k, m)
+        assert np.array_equal(got["h1"], O.s1_hist(rd, k))
+        assert np.array_equal(got["counting"], exp_ec)
+        n = O.solid_bytes(rd, k)
+        assert np.array_equal(got["is_solid"][:n], exp_solid[:n])
+    stream, meta, totals = O.stage2(rd, k, m, exp_solid)
+    assert np.array_equal(got["h2"], O.s2_hist(rd, k, m, exp_solid if exp_solid is not None else np.zeros(8, np.uint8)))
+    assert np.array_equal(got["meta"], meta)
+    assert np.array_equal(got["totals"], totals)
+    assert got["stream"] == stream
+
+
+def check_vs_golden(got, g):
+    assert len(got["stream"]) == g["stream_bytes"]
+    assert O.stream_hash(got["stream"]) == g["stream_hash"]
+    assert O.meta_hash(got["meta"]) == g["meta_hash"]
+    assert [int(x) for x in got["totals"][:9]] == g["num_w"]
+    if g["m"] > 1:
+        txt = O.counting_text(got["counting"])
+        assert hashlib.sha256(txt.encode()).hexdigest()[:16] == g["counting_sha"]
+
+
+ORACLE_CASES = [("tiny", 21, 1), ("tiny", 25, 2), ("tiny", 13, 2), ("smoke", 31, 2), ("smoke", 21, 2), ("smoke", 32, 2),
+                ("smoke", 41, 3), ("smoke", 61, 2), ("smoke", 99, 2), ("smoke", 63, 1), ("smoke", 127, 2),
+                ("adversarial", 31, 2), ("adversarial", 17, 2), ("adversarial", 48, 2), ("adversarial", 21, 1),
+                ("xander", 29, 1), ("xander", 44, 2)]
+
+
+@pytest.mark.parametrize("ds,k,m", ORACLE_CASES)
+def test_gpu_matches_oracle(read_lib, ds, k, m):
+    _, rd = read_lib(ds)
+    check_vs_oracle(rd, k, m, run_gpu(rd, k, m))
+
+
+@pytest.mark.parametrize("ds,k,m,cap", [("smoke", 31, 2, 256), ("adversarial", 31, 2, 128), ("adversarial", 21, 1, 64),
+                                        ("tiny", 25, 2, 64), ("smoke", 61, 2, 512)])
+def test_gpu_small_tiles_force_msd_levels_and_giants(read_lib, ds, k, m, cap):
+    """A tiny on-chip tile makes every bucket oversize: exercises all MSD levels and the counted giant groups."""
+    _, rd = read_lib(ds)
+    got = run_gpu(rd, k, m, sort_items_cap=cap)
+    check_vs_oracle(rd, k, m, got)
+    assert got["stats2"]["msd_levels"] >= 1
+
+
+@pytest.mark.parametrize("ds,k,m,budget", [("smoke", 31, 2, 24 << 20), ("adversarial", 27, 3, 16 << 20)])
+def test_gpu_small_hbm_budget_forces_batches(read_lib, ds, k, m, budget):
+    _, rd = read_lib(ds)
+    got = run_gpu(rd, k, m, hbm_budget_bytes=budget)
+    check_vs_oracle(rd, k, m, got)
+    assert got["stats2"]["n_batches"] > 1
+
+
+GOLDEN_CASES = ["smoke_k31_m2", "smoke_k21_m2", "smoke_k22_m2", "smoke_k32_m2", "smoke_k41_m2", "smoke_k61_m2",
+                "smoke_k99_m2", "smoke_k31_m1", "smoke_k31_m3", "xander_k29_m1", "xander_k44_m1", "adversarial_k31_m2",
+                "adversarial_k21_m1", "adversarial_k27_m3", "adversarial_k30_m2", "adversarial_k48_m2",
+                "adversarial_k17_m2", "tiny_k21_m1", "tiny_k25_m2", "meta200k_k31_m2", "meta200k_k61_m2",
+                "meta200k_k21_m3", "meta1m_k31_m2"]
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_gpu_matches_reference_golden(case, golden, read_lib):
+    g = golden["cases"][case]
+    _, rd = read_lib(g["dataset"])
+    check_vs_golden(run_gpu(rd, g["k"], g["m"]), g)
+
+
+def test_gpu_shards_concatenate_to_the_whole_graph(read_lib):
+    """world-way bucket sharding on one device: shard streams concatenate to the 1-way stream."""
+    _, rd = read_lib("smoke")
+    k, m = 31, 2
+    whole = run_gpu(rd, k, m)
+    for world in (2, 3, 8):
+        ctxs = [cabi.Context(k, m, rank=r, world=world) for r in range(world)]
+        try:
+            solid = None
+            ec = np.zeros(65536, dtype=np.int64)
+            for c in ctxs:
+                c.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+                ec += c.stage1()
+                s = c.get_is_solid()
+                solid = s if solid is None else (solid | s)
+            assert np.array_equal(ec, whole["counting"])
+            streams, meta = [], np.zeros((65536, 3), dtype=np.int64)
+            totals = np.zeros(10, dtype=np.int64)
+            for c in ctxs:
+                c.set_is_solid(solid)
+                st, mt, tt = c.stage2()
+                streams.append(st)
+                meta += mt
+                totals += tt
+            assert b"".join(streams) == whole["stream"]
+            assert np.array_equal(meta, whole["meta"])
+            assert np.array_equal(totals, whole["totals"])
+        finally:
+            for c in ctxs:
+                c.close()

@@ -1,0 +1,84 @@
+"""CPU tests of the product's __host__ __device__ item/emission logic (kmer_ops.cuh, cx1_items.cuh,
+cx1_emit.cuh) driven by tests/cpu/logic_host.cpp, against the oracle.  Sorting is std::sort here; the
+device sort is covered by the gpu tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpu", "logic_host.cpp")
+OUT = os.path.join(ROOT, "tests", "cpu", "_build", "liblogic_host.so")
+
+
+@pytest.fixture(scope="session")
+def logic():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    deps = [SRC] + [os.path.join(ROOT, "megagta_b200", "csrc", f) for f in ("kmer_ops.cuh", "cx1_items.cuh", "cx1_emit.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", OUT, SRC],
+                       check=True)
+    return ctypes.CDLL(OUT)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_logic(lib, rd, k, m, mercy):
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
+    is_solid = np.zeros(O.solid_bytes(rd, k) + 8, dtype=np.uint8)
+    ec = np.zeros(65536, dtype=np.int64)
+    h1 = np.zeros(65536, dtype=np.int64)
+    cands = np.empty(0, dtype=np.uint64)
+    if m > 1:
+        cp, cn = ctypes.c_void_p(), ctypes.c_int64()
+        assert lib.logic_stage1(_p(rd["seq"]), _p(rd["start"]), n, ns, rd["max_len"], k, m, _p(is_solid), _p(ec),
+                                int(mercy), ctypes.byref(cp), ctypes.byref(cn), _p(h1)) == 0
+        cands = np.empty(cn.value, dtype=np.uint64)
+        if cn.value:
+            ctypes.memmove(_p(cands), cp, cn.value * 8)
+        lib.logic_free(cp)
+        if mercy:
+            O.mercy(rd, k, is_solid, cands)
+    sp, sn = ctypes.c_void_p(), ctypes.c_int64()
+    meta = np.zeros((65536, 3), dtype=np.int64)
+    totals = np.zeros(10, dtype=np.int64)
+    h2 = np.zeros(65536, dtype=np.int64)
+    assert lib.logic_stage2(_p(rd["seq"]), _p(rd["start"]), n, ns, rd["max_len"], k, m, _p(is_solid), ctypes.byref(sp),
+                            ctypes.byref(sn), _p(meta), _p(totals), _p(h2)) == 0
+    stream = ctypes.string_at(sp, sn.value)
+    lib.logic_free(sp)
+    return dict(stream=stream, meta=meta, totals=totals, counting=ec, is_solid=is_solid, cands=cands, h1=h1, h2=h2)
+
+
+CASES = [("tiny", 21, 1, False), ("tiny", 25, 2, True), ("tiny", 13, 2, False),
+         ("smoke", 31, 2, False), ("smoke", 31, 2, True), ("smoke", 21, 2, False), ("smoke", 32, 2, False),
+         ("smoke", 41, 3, True), ("smoke", 61, 2, False), ("smoke", 99, 2, False), ("smoke", 63, 1, False),
+         ("adversarial", 31, 2, True), ("adversarial", 17, 2, False), ("adversarial", 48, 2, False),
+         ("adversarial", 27, 3, True), ("adversarial", 64, 2, True), ("adversarial", 21, 1, False)]
+
+
+@pytest.mark.parametrize("ds,k,m,mercy", CASES)
+def test_device_logic_on_cpu_matches_oracle(logic, read_lib, ds, k, m, mercy):
+    _, rd = read_lib(ds)
+    got = run_logic(logic, rd, k, m, mercy)
+    exp_solid = exp_ec = None
+    exp_cands = np.empty(0, dtype=np.uint64)
+    if m > 1:
+        exp_solid, exp_ec, exp_cands = O.stage1(rd, k, m, mercy)
+        assert np.array_equal(got["h1"], O.s1_hist(rd, k))
+        assert np.array_equal(got["counting"], exp_ec)
+        assert np.array_equal(got["cands"], exp_cands)
+        if mercy:
+            O.mercy(rd, k, exp_solid, exp_cands)
+        assert np.array_equal(got["is_solid"][:len(exp_solid)], exp_solid)
+    stream, meta, totals = O.stage2(rd, k, m, exp_solid)
+    assert np.array_equal(got["h2"], O.s2_hist(rd, k, m, exp_solid if exp_solid is not None else np.zeros(8, np.uint8)))
+    assert got["stream"] == stream
+    assert np.array_equal(got["meta"], meta)
+    assert np.array_equal(got["totals"], totals)
