@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- SdBG edges/s of the CX1 reads->SdBG path on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (libmgta_cuda.so via its C ABI)
+  python bench.py --impl reference [--gpus N] ...                 the reference's CPU CX1 on the host cores
+
+One "step" = one whole buildgraph (stage 1 + stage 2) over the synthetic read set.
+  value : inputs resident in HBM, records left in HBM (device work only)
+  e2e   : the same call chain from HOST buffers: H2D of the packed reads (+ NCCL broadcast when N>1),
+          both stages, D2H of the record stream and the per-bucket table, every step
+Workload at N GPUs: 20M x N reads of 150 bp (weak scaling; N=1 is BASELINE.json configs[1]), k=31, m=2.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "SdBG edges/sec"
+UNIT = "edges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads-per-gpu", type=int, default=20_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("-k", type=int, default=31)
+    ap.add_argument("-m", type=int, default=2)
+    ap.add_argument("--sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=20261017)
+    return ap.parse_args()
+
+
+def workload_name(a, n_gpus):
+    return "%dM x %d bp synthetic metagenome reads, k=%d, min-count %d" % (
+        a.reads_per_gpu * n_gpus // 1_000_000, a.read_len, a.k, a.m)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def auto_sample(a):
+    if a.sample_reads:
+        return a.sample_reads
+    cores = os.cpu_count() or 1
+    return min(a.reads_per_gpu, 1_000_000 if cores <= 16 else 2_000_000)
+
+
+def write_sample(a, work):
+    from megagta_b200 import synth
+    n = auto_sample(a)
+    prefix = os.path.join(work, "sample")
+    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n)
+    return prefix, n
+
+
+def time_reference(prefix, a, work, tag):
+    """One run of the unmodified reference buildgraph (oracle/_ref) on all host cores -> (seconds, edges, kind)."""
+    from oracle import oracle as O
+    from megagta_b200 import sdbg_io
+    cores = os.cpu_count() or 2
+    out = os.path.join(work, "ref_" + tag)
+    if O.have_ref():
+        t = time.time()
+        O.run_ref_buildgraph(prefix, out, a.k, a.m, threads=max(2, cores))
+        dt = time.time() - t
+        hdr, _ = sdbg_io.read_info(out)
+        for f in os.listdir(work):
+            if f.startswith("ref_" + tag):
+                os.remove(os.path.join(work, f))
+        return dt, hdr["total_size"], "reference", max(2, cores)
+    rd = O.load_read_lib(prefix)                      # fall back to the single-threaded C restatement
+    t = time.time()
+    res = O.build_graph(rd, a.k, a.m)
+    return time.time() - t, int(res["meta"][:, 0].sum()), "port", 1
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    work = tempfile.mkdtemp(prefix="mgta_bench_ref_")
+    prefix, n = write_sample(a, work)
+    times, edges, kind, cores = [], 0, "reference", 1
+    for i in range(a.warmup + a.steps):
+        dt, edges, kind, cores = time_reference(prefix, a, work, str(i))
+        if i >= a.warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    value = edges / (ms / 1000.0)
+    sample = "first %d reads of the workload (%d x %d bp), whole buildgraph, %d threads" % (n, n, a.read_len, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(a, a.gpus), "sample": sample, "edges_per_step": edges},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.stop_flag, self.rows = dev, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+class DevBuf:
+    def __init__(self, ptr, nbytes, typestr="<i4", itemsize=4):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    from megagta_b200 import cabi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_gpus = world
+    n_reads = a.reads_per_gpu * n_gpus
+    L = a.read_len
+
+    # ---- synthetic reads (rank 0 only; the other ranks receive them over NVLink)
+    work = tempfile.mkdtemp(prefix="mgta_bench_")
+    sample_prefix, sample_n = os.path.join(work, "sample"), auto_sample(a)
+    n_words = n_reads * L // 16 + 1
+    if rank == 0:
+        t0 = time.time()
+        seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix, bin_reads=sample_n)
+        seq_pin = torch.from_numpy(seq).pin_memory()
+        start_pin = torch.from_numpy(start.view(np.int64)).pin_memory()
+        del seq, start
+        gen_s = time.time() - t0
+    stream = torch.cuda.Stream(device=dev)
+    ctx = cabi.Context(a.k, a.m, device=local, rank=rank, world=world, stream=stream.cuda_stream)
+
+    def load_reads():
+        """host -> HBM (+ broadcast).  Returns H2D bytes."""
+        h2d = 0
+        if rank == 0:
+            ctx._check(ctx.lib.mgta_set_reads(ctx.h, seq_pin.data_ptr(), n_words, start_pin.data_ptr(), n_reads, n_reads, L),
+                       "mgta_set_reads")
+            ctx.n_short, ctx.max_len = n_reads, L
+            h2d = n_words * 4 + (n_reads + 1) * 8
+        else:
+            ctx.alloc_reads(n_words, n_reads, n_reads, n_reads * L, L)
+        if world > 1:
+            (sp, sb), (tp, tb) = ctx.reads_device_buffers()
+            dist.broadcast(torch.as_tensor(DevBuf(sp, sb), device=dev), 0)
+            dist.broadcast(torch.as_tensor(DevBuf(tp, tb), device=dev), 0)
+        return h2d
+
+    def merge_solid():
+        if world > 1 and a.m > 1:
+            p, nb = ctx.solid_device_buffer()
+            dist.all_reduce(torch.as_tensor(DevBuf(p, nb), device=dev), op=dist.ReduceOp.SUM)
+
+    def step(e2e):
+        """-> (edges of this shard, h2d bytes, d2h bytes)"""
+        h2d = load_reads() if e2e else 0
+        d2h = 0
+        if a.m > 1:
+            ctx.stage1()
+            merge_solid()
+        if e2e:
+            nbytes, meta, totals = ctx.stage2(collect="count")
+            d2h = nbytes + meta[slice(*ctx.shard_range())].nbytes
+        else:
+            ctx.stage2(collect=False)
+        return ctx.stats(2)["n_edges"], h2d, d2h
+
+    def timed(fn, reps):
+        """barrier + sync, CUDA events on the launching stream, max over ranks -> ms per rep"""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        outs = [fn() for _ in range(reps)]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / reps, outs
+
+    with torch.cuda.stream(stream):
+        load_reads()
+        for _ in range(a.warmup):
+            step(False)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms_dev, outs = timed(lambda: step(False), a.steps)
+        st1, st2 = ctx.stats(1), ctx.stats(2)
+        ms_e2e, outs_e2e = timed(lambda: step(True), a.steps)
+        sampler.stop_flag = True
+        sampler.join()
+
+    def total(x):
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    edges = total(outs[-1][0])
+    h2d = total(outs_e2e[-1][1])
+    d2h = total(outs_e2e[-1][2])
+    launches = total(st1["n_launches"] + st2["n_launches"]) * a.steps
+
+    if rank == 0:
+        peaks = {}
+        pk_src = "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            pk_src = "measured"
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # per-kernel algorithmic bytes: each kernel reads and writes every byte it must, once
+        seq_bytes = n_words * 4
+        kern = []
+        for sname, st in (("s1", st1), ("s2", st2)):
+            n, iw = st["n_items"], st["item_words"]
+            if not n:
+                continue
+            kern.append((sname + ".hist(k_walk)", st["ms_hist"], seq_bytes + 65536 * 8))
+            kern.append((sname + ".extract(k_walk)", st["ms_extract"], seq_bytes * max(1, st["n_batches"]) + n * iw * 4))
+            if st["ms_partition"] > 0:
+                kern.append((sname + ".partition(k_msd)", st["ms_partition"], n * (4 + 2 * iw * 4)))
+            kern.append((sname + ".sort_emit(k_chunk)", st["ms_sort_emit"], n * iw * 4 + st["out_bytes"]))
+        kern.sort(key=lambda x: -x[1])
+        top = kern[0]
+        ach = top[2] / (top[1] / 1000.0) / 1e9 if top[1] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": pk_src, "algorithmic_bytes_per_launch": top[2],
+                    "kernels": [{"name": k[0], "ms": k[1], "bytes": k[2], "gbs": (k[2] / (k[1] / 1000.0) / 1e9 if k[1] > 0 else 0.0)}
+                                for k in kern]}
+        # bytes the reference's LSD model would move per item vs what the kernels above move
+        cpu_baseline = None
+        if n_gpus == 1 and not a.no_cpu_baseline:
+            dt, e, kind, cores = time_reference(sample_prefix, a, work, "cpu")
+            cpu_baseline = {"value": e / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
+                            "sample": "first %d reads of the workload (%d x %d bp), whole buildgraph" % (sample_n, sample_n, L)}
+        line = {"metric": METRIC, "value": edges / (ms_dev / 1000.0), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic",
+                "config": {"workload": workload_name(a, n_gpus), "reads": n_reads, "read_len": L, "k": a.k, "min_count": a.m,
+                           "edges_per_step": edges, "s1_items": total_items(st1, world, dist, dev, torch),
+                           "s2_items": total_items(st2, world, dist, dev, torch),
+                           "l2": "inputs larger than L2 (item arrays are GBs per step); no explicit flush",
+                           "sharding": "contiguous lv1-bucket ranges, %d shard(s)" % world, "gen_seconds": gen_s},
+                "e2e": {"value": edges / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+                "stage_ms": {"s1": st1["ms_total"], "s2": st2["ms_total"]},
+                "stats": {"s1": st1, "s2": st2}}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    else:
+        total_items(st1, world, dist, dev, torch)
+        total_items(st2, world, dist, dev, torch)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def total_items(st, world, dist, dev, torch):
+    t = torch.tensor([float(st["n_items"])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+if __name__ == "__main__":
+    main()

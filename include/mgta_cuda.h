@@ -94,6 +94,15 @@ const char *mgta_last_error(const mgta_ctx *ctx); /* ctx may be NULL: last creat
 int mgta_set_reads(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_t n_words, const uint64_t *start_idx,
                    uint64_t n_reads, uint64_t n_short_reads, int32_t max_read_len);
 
+/* Multi-GPU read distribution (north star: "packed reads are broadcast with NCCL over NVLink"):
+ * a non-root shard allocates device buffers of the right size, the caller broadcasts the root's
+ * buffers into them (ncclBroadcast / torch.distributed.broadcast) and no host copy is needed.
+ * seq buffer = n_words u32 (+ zero padding owned by the library), start buffer = (n_reads+1) u64. */
+int mgta_alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_short_reads,
+                     uint64_t total_bases, int32_t max_read_len);
+int mgta_reads_device_buffers(mgta_ctx *ctx, void **seq_dev, uint64_t *seq_bytes, void **start_dev,
+                              uint64_t *start_bytes);
+
 /* lv1 bucket histograms (reference s1_lv0_calc_bucket_size s1.cpp:177-229 and
  * s2_lv0_calc_bucket_size s2.cpp:252-315).  hist: int64[65536], whole bucket space. */
 int mgta_stage1_histogram(mgta_ctx *ctx, int64_t *hist);

@@ -36,7 +36,8 @@ class StageStats(ctypes.Structure):
 SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                         ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64))
 
-EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_stage1_histogram",
+EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_alloc_reads",
+           "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
            "mgta_get_mercy_candidates", "mgta_stage2", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version"]
@@ -57,6 +58,11 @@ def load():
         lib.mgta_ctx_destroy.restype = None
         lib.mgta_set_reads.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
                                        ctypes.c_uint64, ctypes.c_int32]
+        lib.mgta_alloc_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.c_int32]
+        lib.mgta_reads_device_buffers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                  ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_void_p),
+                                                  ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_stage1_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage2_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage1.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -118,6 +124,16 @@ class Context:
         self.n_short, self.max_len = n_short, max_len
         self._check(self.lib.mgta_set_reads(self.h, _p(seq), len(seq), _p(start), n, n_short, max_len), "mgta_set_reads")
 
+    def alloc_reads(self, n_words, n_reads, n_short, total_bases, max_len):
+        self.n_short, self.max_len = n_short, max_len
+        self._check(self.lib.mgta_alloc_reads(self.h, n_words, n_reads, n_short, total_bases, max_len), "mgta_alloc_reads")
+
+    def reads_device_buffers(self):
+        a, an, b, bn = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self.lib.mgta_reads_device_buffers(self.h, ctypes.byref(a), ctypes.byref(an), ctypes.byref(b),
+                                                       ctypes.byref(bn)), "mgta_reads_device_buffers")
+        return (a.value, an.value), (b.value, bn.value)
+
     def histogram(self, stage):
         h = np.zeros(NUM_BUCKETS, dtype=np.int64)
         fn = self.lib.mgta_stage1_histogram if stage == 1 else self.lib.mgta_stage2_histogram
@@ -154,20 +170,26 @@ class Context:
         return out
 
     def stage2(self, collect=True):
-        """-> (stream bytes, meta int64[65536,3], totals int64[10]).  collect=False keeps the records on the device."""
+        """-> (stream bytes, meta int64[65536,3], totals int64[10]).
+        collect=True   copy every delivery into one Python bytes object (tests, file writers)
+        collect="count" the library still copies records + table to pinned host memory each batch, the sink only
+                       counts them (bench e2e: no extra Python-side memcpy); stream is returned as its length
+        collect=False  records stay on the device (sink = NULL)"""
         parts = []
+        nbytes_total = [0]
         meta = np.zeros((NUM_BUCKETS, 3), dtype=np.int64)
 
         def sink(user, b0, b1, ptr, nbytes, mptr):
-            if nbytes:
+            if nbytes and collect is True:
                 parts.append(ctypes.string_at(ptr, nbytes))
+            nbytes_total[0] += nbytes
             meta[b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
             return 0
 
         cb = SINK(sink) if collect else ctypes.cast(None, SINK)
         totals = np.zeros(10, dtype=np.int64)
         self._check(self.lib.mgta_stage2(self.h, cb, None, _p(totals)), "mgta_stage2")
-        return b"".join(parts), meta, totals
+        return (b"".join(parts) if collect is True else nbytes_total[0]), meta, totals
 
     def shard_range(self):
         a, b = ctypes.c_int32(), ctypes.c_int32()

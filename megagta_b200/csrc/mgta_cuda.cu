@@ -247,29 +247,58 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     delete ctx;
 }
 
+namespace {
+int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_short, uint64_t total, int max_len) {
+    if (n_reads == 0 || n_short > n_reads) FAIL(MGTA_ERR_ARG, "reads: bad counts");
+    if (total == 0) FAIL(MGTA_ERR_ARG, "reads: no bases");
+    if (n_words * 16 < total) FAIL(MGTA_ERR_ARG, "reads: packed_seq shorter than start_idx says");
+    if (total >= (1ull << 40) - 1) FAIL(MGTA_ERR_ARG, "reads: more than 2^40 bases");
+    CK(cudaSetDevice(ctx->opt.device));
+    const uint64_t padded = ((n_words + 3) & ~3ull) + SEQ_PAD_WORDS;
+    const uint64_t solid_words = (total + 31) / 32 + 4;
+    if (n_words != ctx->n_words || n_reads != ctx->n_reads || total != ctx->total_bases || !ctx->d_seq) {     // reuse buffers of equal shape
+        cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
+        ctx->d_seq = nullptr; ctx->d_start = nullptr; ctx->d_solid = nullptr;
+        CK(cudaMalloc(&ctx->d_seq, padded * 4));
+        CK(cudaMalloc(&ctx->d_start, (n_reads + 1) * 8));
+        CK(cudaMalloc(&ctx->d_solid, solid_words * 4));
+    }
+    ctx->solid_words = solid_words;
+    CK(cudaMemsetAsync(ctx->d_seq + n_words, 0, (padded - n_words) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
+    ctx->n_words = n_words; ctx->n_reads = n_reads; ctx->n_short = n_short; ctx->total_bases = total;
+    ctx->max_len = max_len;
+    return MGTA_OK;
+}
+}  // namespace
+
 extern "C" int mgta_set_reads(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_t n_words, const uint64_t *start_idx,
                               uint64_t n_reads, uint64_t n_short_reads, int32_t max_read_len) {
     if (!ctx) return MGTA_ERR_ARG;
-    if (!packed_seq || !start_idx || n_reads == 0 || n_short_reads > n_reads) FAIL(MGTA_ERR_ARG, "set_reads: bad arguments");
-    const uint64_t total = start_idx[n_reads];
-    if (total == 0) FAIL(MGTA_ERR_ARG, "set_reads: no bases");
-    if (n_words * 16 < total) FAIL(MGTA_ERR_ARG, "set_reads: packed_seq shorter than start_idx says");
-    if (total >= (1ull << 40) - 1) FAIL(MGTA_ERR_ARG, "set_reads: more than 2^40 bases");
-    CK(cudaSetDevice(ctx->opt.device));
-    cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
-    ctx->d_seq = nullptr; ctx->d_start = nullptr; ctx->d_solid = nullptr;
-    const uint64_t padded = ((n_words + 3) & ~3ull) + SEQ_PAD_WORDS;
-    CK(cudaMalloc(&ctx->d_seq, padded * 4));
-    CK(cudaMalloc(&ctx->d_start, (n_reads + 1) * 8));
-    ctx->solid_words = (total + 31) / 32 + 4;
-    CK(cudaMalloc(&ctx->d_solid, ctx->solid_words * 4));
-    CK(cudaMemsetAsync(ctx->d_seq + n_words, 0, (padded - n_words) * 4, ctx->stream));
+    if (!packed_seq || !start_idx || n_reads == 0) FAIL(MGTA_ERR_ARG, "set_reads: bad arguments");
+    int rc = alloc_reads(ctx, n_words, n_reads, n_short_reads, start_idx[n_reads], max_read_len);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_seq, packed_seq, n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_start, start_idx, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_words = n_words; ctx->n_reads = n_reads; ctx->n_short = n_short_reads; ctx->total_bases = total;
-    ctx->max_len = max_read_len;
+    return MGTA_OK;
+}
+
+extern "C" int mgta_alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_short_reads,
+                                uint64_t total_bases, int32_t max_read_len) {
+    if (!ctx) return MGTA_ERR_ARG;
+    int rc = alloc_reads(ctx, n_words, n_reads, n_short_reads, total_bases, max_read_len);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MGTA_OK;
+}
+
+extern "C" int mgta_reads_device_buffers(mgta_ctx *ctx, void **seq_dev, uint64_t *seq_bytes, void **start_dev,
+                                         uint64_t *start_bytes) {
+    if (!ctx || !seq_dev || !seq_bytes || !start_dev || !start_bytes) return MGTA_ERR_ARG;
+    if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads or mgta_alloc_reads first");
+    *seq_dev = ctx->d_seq; *seq_bytes = ctx->n_words * 4;
+    *start_dev = ctx->d_start; *start_bytes = (ctx->n_reads + 1) * 8;
     return MGTA_OK;
 }
 

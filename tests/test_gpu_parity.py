@@ -63,7 +63,7 @@ def test_gpu_matches_oracle(read_lib, ds, k, m):
 
 
 @pytest.mark.parametrize("ds,k,m,cap", [("smoke", 31, 2, 256), ("adversarial", 31, 2, 128), ("adversarial", 21, 1, 64),
-                                        ("tiny", 25, 2, 64), ("smoke", 61, 2, 512)])
+                                        ("tiny", 25, 2, 64), ("smoke", 61, 2, 64)])
 def test_gpu_small_tiles_force_msd_levels_and_giants(read_lib, ds, k, m, cap):
     """A tiny on-chip tile makes every bucket oversize: exercises all MSD levels and the counted giant groups."""
     _, rd = read_lib(ds)
