@@ -59,16 +59,12 @@ MGTA_HD void s1_position(const uint32_t *words, uint32_t q, uint64_t g, int p, i
     }
 }
 
-// Caller guarantees L >= k+1, o < L-k and solid(o).  emit(key[W])
+// The <= 6 stage-2 items of one solid edge E (k+1 chars, zero padded, W = key_words_s2(k) words) with
+// R = rc(E), pal = (E == R).  `left` / `right`: also emit the $-items of the edge's first / last k-mer.
+// emit(key[W])
 template <int W, class Emit>
-MGTA_HD void s2_position(const uint32_t *words, uint32_t q, int o, int L, int k, bool solid_prev, bool solid_next,
-                         Emit &&emit) {
-    uint32_t E[W], R[W];
-    load_chars<W>(words, q, k + 1, E);
-    revcomp<W>(E, k + 1, R);
-    const bool pal = cmp_words<W>(E, R) == 0;
-    const bool left = (o == 0) || !solid_prev;
-    const bool right = (o == L - k - 1) || !solid_next;
+MGTA_HD void s2_edge_items(const uint32_t (&E)[W], const uint32_t (&R)[W], bool pal, bool left, bool right, int k,
+                           Emit &&emit) {
     auto put = [&](const uint32_t(&X)[W], int c, bool has_a) {
         uint32_t Y[W];
         sub_chars<W>(X, c, has_a ? k : k - 1, Y);
@@ -86,6 +82,46 @@ MGTA_HD void s2_position(const uint32_t *words, uint32_t q, int o, int L, int k,
         put(E, 2, false);
         if (!pal) put(R, 0, true);
     }
+}
+
+// Caller guarantees L >= k+1, o < L-k and solid(o).  emit(key[W])
+template <int W, class Emit>
+MGTA_HD void s2_position(const uint32_t *words, uint32_t q, int o, int L, int k, bool solid_prev, bool solid_next,
+                         Emit &&emit) {
+    uint32_t E[W], R[W];
+    load_chars<W>(words, q, k + 1, E);
+    revcomp<W>(E, k + 1, R);
+    const bool pal = cmp_words<W>(E, R) == 0;
+    s2_edge_items<W>(E, R, pal, (o == 0) || !solid_prev, (o == L - k - 1) || !solid_next, k, emit);
+}
+
+// ---- edge-centric path (v2).  An EDGE is a (k+1)-mer; its canonical form is min(e, rc(e)) as zero padded
+// words.  Stage 1 without mercy only needs the multiset of canonical edges (s1.cpp:744-760 count
+// (head, S, tail) groups, whose strand rule s1.cpp:482-495 is one particular canonical form: any
+// other gives the same counts and the same solid occurrences); stage 2's records are a function of
+// {(oriented edge, number of solid occurrences)}.
+MGTA_HD int edge_words(int k) { return (2 * (k + 1) + 31) / 32; }
+
+template <int WE>
+MGTA_HD void canonical_edge(const uint32_t *words, uint32_t q, int k, uint32_t (&key)[WE]) {
+    uint32_t E[WE], R[WE];
+    load_chars<WE>(words, q, k + 1, E);
+    revcomp<WE>(E, k + 1, R);
+    const bool fw = cmp_words<WE>(E, R) <= 0;
+#pragma unroll
+    for (int w = 0; w < WE; ++w) key[w] = fw ? E[w] : R[w];
+}
+
+// all stage-2 items of a canonical edge (both orientations, $-items unconditionally: the emission
+// rules s2.cpp:801-818 drop a $-item whenever a real edge covers it, which is exactly the case in
+// which the reference would not have produced it at every occurrence).  W = key_words_s2(k) >= WE.
+template <int W, int WE, class Emit>
+MGTA_HD void s2_items_of_edge(const uint32_t (&key)[WE], int k, Emit &&emit) {
+    uint32_t E[W], R[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) E[w] = w < WE ? key[w < WE ? w : 0] : 0u;
+    revcomp<W>(E, k + 1, R);
+    s2_edge_items<W>(E, R, cmp_words<W>(E, R) == 0, true, true, k, emit);
 }
 
 }  // namespace mgta

@@ -189,3 +189,123 @@ int logic_stage2(const uint32_t *seq, const uint64_t *start, int64_t n_reads, in
 }
 void logic_free(void *p) { free(p); }
 }
+
+// ---- edge-centric path (v2): canonical (k+1)-mer multiset -> stage-1 outputs, and
+// {(canonical edge, solid occurrences)} -> stage-2 records with multiplicity-weighted runs.
+#include <map>
+#include <array>
+typedef std::array<uint32_t, 9> EKey;
+
+template <int WE>
+static void count_edges_t(const Reads &rd, const uint8_t *is_solid_filter, std::map<EKey, std::pair<uint32_t, uint32_t>> &tab,
+                          std::vector<std::pair<EKey, uint64_t>> *occ) {
+    const int k = rd.k; const int64_t nk1 = rd.max_len - k;
+    for (int64_t r = 0; r < rd.n_reads; ++r) {
+        uint64_t s = rd.start[r]; int L = (int)(rd.start[r + 1] - s);
+        if (L < k + 1) continue;
+        const bool assist = r >= rd.n_short;
+        for (int o = 0; o < L - k; ++o) {
+            if (is_solid_filter) {
+                int64_t bit = nk1 * r + o;
+                if (!(rd.m == 1 || assist || ((is_solid_filter[bit >> 3] >> (bit & 7)) & 1))) continue;
+            }
+            uint64_t g = s + o; uint64_t w0 = (g >> 4) >= 4 ? (g >> 4) - 4 : 0;
+            uint32_t key[WE];
+            canonical_edge<WE>(rd.seq + w0, (uint32_t)(g - 16 * w0), k, key);
+            EKey ek; ek.fill(0); for (int w = 0; w < WE; ++w) ek[w] = key[w];
+            auto &c = tab[ek]; c.first++; if (assist) c.second++;
+            if (occ && !assist) occ->push_back({ek, (uint64_t)(nk1 * r + o)});
+        }
+    }
+}
+
+template <int W> struct Item2W { uint32_t key[W]; uint32_t mult; };
+
+template <int W, int WE>
+static void emit_edges_t(const Reads &rd, const std::map<EKey, std::pair<uint32_t, uint32_t>> &tab, bool apply_threshold, Out2 &out) {
+    const int k = rd.k;
+    std::vector<Item2W<W>> items;
+    for (auto &kv : tab) {
+        uint32_t mult = apply_threshold ? (kv.second.first >= (uint32_t)rd.m ? kv.second.first : kv.second.second) : kv.second.first;
+        if (!mult) continue;
+        uint32_t key[WE]; for (int w = 0; w < WE; ++w) key[w] = kv.first[w];
+        s2_items_of_edge<W, WE>(key, k, [&](const uint32_t(&y)[W]) { Item2W<W> it; memcpy(it.key, y, sizeof(it.key)); it.mult = mult; items.push_back(it); });
+    }
+    std::sort(items.begin(), items.end(), [](const Item2W<W> &a, const Item2W<W> &b) {
+        for (int i = 0; i < W; ++i) if (a.key[i] != b.key[i]) return a.key[i] < b.key[i];
+        return false;
+    });
+    const int full = (k - 1) / 16, rem = (k - 1) % 16;
+    const int aw = (k - 1) >> 4, ash = (15 - ((k - 1) & 15)) * 2;
+    auto same_group = [&](const Item2W<W> &a, const Item2W<W> &b) {
+        for (int w = 0; w < full; ++w) if (a.key[w] != b.key[w]) return false;
+        if (rem && (a.key[full] >> (16 - rem) * 2) != (b.key[full] >> (16 - rem) * 2)) return false;
+        return true;
+    };
+    struct Runs {
+        const std::vector<Item2W<W>> *it; size_t i, e, cur; int aw, ash;
+        void reset() { cur = i; }
+        bool next(S2Run &r) {
+            if (cur >= e) return false;
+            const Item2W<W> &x = (*it)[cur];
+            size_t j = cur; uint64_t sum = 0;
+            while (j < e && memcmp((*it)[j].key, x.key, sizeof(x.key)) == 0) { sum += (*it)[j].mult; ++j; }
+            uint32_t lw = x.key[W - 1];
+            r.a = (lw >> 3 & 1) ? (int)((x.key[aw] >> ash) & 3) : SENT; r.b = lw & 7; r.cnt = (uint32_t)std::min<uint64_t>(sum, 0xFFFFFFFFu); r.item = (uint32_t)cur;
+            cur = j; return true;
+        }
+    };
+    struct Sink {
+        Out2 *o; const std::vector<Item2W<W>> *it;
+        void record(int w, int last, int tip, uint32_t mult, uint32_t item) {
+            const Item2W<W> &x = (*it)[item];
+            int bucket = x.key[0] >> 16;
+            uint16_t rec = s2_record_word(w, last, tip, mult);
+            o->bytes.insert(o->bytes.end(), (uint8_t *)&rec, (uint8_t *)&rec + 2);
+            o->meta[bucket * 3]++; o->totals[w]++; o->totals[9] += last;
+            if (mult > 254) { uint16_t mm = (uint16_t)mult; o->bytes.insert(o->bytes.end(), (uint8_t *)&mm, (uint8_t *)&mm + 2); o->meta[bucket * 3 + 2]++; }
+            if (tip) { o->bytes.insert(o->bytes.end(), (uint8_t *)x.key, (uint8_t *)x.key + 4 * o->wpt); o->meta[bucket * 3 + 1]++; }
+        }
+    };
+    size_t n = items.size();
+    for (size_t i = 0, e; i < n; i = e) {
+        for (e = i + 1; e < n && same_group(items[i], items[e]); ++e) {}
+        Runs runs{&items, i, e, i, aw, ash};
+        Sink sink{&out, &items};
+        s2_emit_group(runs, sink);
+    }
+}
+
+#define DISPATCH2(W, WE, CALL) DISPATCH(W, { constexpr int W2 = WW; if (WE == W2) { constexpr int WEE = W2; CALL; } else { constexpr int WEE = W2 > 1 ? W2 - 1 : 1; CALL; } })
+
+extern "C" {
+// stage 1 from the canonical-edge multiset: edge_counting + is_solid (reference bit layout)
+int logic_stage1_edges(const uint32_t *seq, const uint64_t *start, int64_t n_reads, int64_t n_short, int max_len, int k, int m,
+                       uint8_t *is_solid, int64_t *edge_counting) {
+    Reads rd{seq, start, n_reads, n_short, max_len, k, m};
+    std::map<EKey, std::pair<uint32_t, uint32_t>> tab;
+    std::vector<std::pair<EKey, uint64_t>> occ;
+    memset(edge_counting, 0, 65536 * 8);
+    DISPATCH(edge_words(k), (count_edges_t<WW>(rd, nullptr, tab, &occ)));
+    for (auto &kv : tab) edge_counting[kv.second.first < 65535 ? kv.second.first : 65535]++;
+    for (auto &o : occ) if (tab[o.first].first >= (uint32_t)m) is_solid[o.second >> 3] |= 1u << (o.second & 7);
+    return 0;
+}
+// stage 2 from {(canonical edge, solid occurrences)}.  fused != 0: take the multiplicities straight from the unfiltered
+// stage-1 counts (count >= m ? count : assist occurrences) instead of re-counting under the is_solid filter.
+int logic_stage2_edges(const uint32_t *seq, const uint64_t *start, int64_t n_reads, int64_t n_short, int max_len, int k, int m,
+                       const uint8_t *is_solid, int fused, uint8_t **stream, int64_t *stream_bytes, int64_t *meta, int64_t *totals) {
+    Reads rd{seq, start, n_reads, n_short, max_len, k, m};
+    Out2 out; out.meta = meta; out.totals = totals; out.wpt = (2 * k + 31) / 32;
+    memset(meta, 0, 65536 * 3 * 8); memset(totals, 0, 10 * 8);
+    std::map<EKey, std::pair<uint32_t, uint32_t>> tab;
+    static uint8_t dummy[8];
+    DISPATCH(edge_words(k), (count_edges_t<WW>(rd, fused ? nullptr : (is_solid ? is_solid : dummy), tab, nullptr)));
+    const int WE = edge_words(k);
+    DISPATCH2(key_words_s2(k), WE, (emit_edges_t<W2, WEE>(rd, tab, fused != 0, out)));
+    *stream = (uint8_t *)malloc(out.bytes.size() + 8);
+    memcpy(*stream, out.bytes.data(), out.bytes.size());
+    *stream_bytes = (int64_t)out.bytes.size();
+    return 0;
+}
+}

@@ -82,3 +82,55 @@ def test_device_logic_on_cpu_matches_oracle(logic, read_lib, ds, k, m, mercy):
     assert got["stream"] == stream
     assert np.array_equal(got["meta"], meta)
     assert np.array_equal(got["totals"], totals)
+
+
+# ---- edge-centric path (v2): the canonical-(k+1)-mer multiset gives stage 1, and {(edge, solid occurrences)} gives stage 2
+def run_edges(lib, rd, k, m, is_solid=None, fused=False):
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
+    sp, sn = ctypes.c_void_p(), ctypes.c_int64()
+    meta = np.zeros((65536, 3), dtype=np.int64)
+    totals = np.zeros(10, dtype=np.int64)
+    sol = is_solid if is_solid is not None else np.zeros(8, dtype=np.uint8)
+    assert lib.logic_stage2_edges(_p(rd["seq"]), _p(rd["start"]), n, ns, rd["max_len"], k, m, _p(sol), int(fused),
+                                  ctypes.byref(sp), ctypes.byref(sn), _p(meta), _p(totals)) == 0
+    stream = ctypes.string_at(sp, sn.value)
+    lib.logic_free(sp)
+    return stream, meta, totals
+
+
+EDGE_CASES = [("tiny", 21, 1, False), ("tiny", 25, 2, True), ("tiny", 13, 2, False), ("tiny", 9, 2, False),
+              ("smoke", 31, 2, False), ("smoke", 31, 2, True), ("smoke", 21, 2, False), ("smoke", 32, 2, False),
+              ("smoke", 41, 3, True), ("smoke", 61, 2, False), ("smoke", 99, 2, False), ("smoke", 63, 1, False),
+              ("smoke", 15, 2, False), ("smoke", 47, 2, False),
+              ("adversarial", 31, 2, True), ("adversarial", 17, 2, False), ("adversarial", 48, 2, False),
+              ("adversarial", 27, 3, True), ("adversarial", 64, 2, True), ("adversarial", 21, 1, False),
+              ("xander", 29, 1, False), ("xander", 44, 2, True)]
+
+
+@pytest.mark.parametrize("ds,k,m,mercy", EDGE_CASES)
+def test_edge_centric_logic_matches_oracle(logic, read_lib, ds, k, m, mercy):
+    _, rd = read_lib(ds)
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
+    exp_solid = None
+    if m > 1:
+        exp_solid, exp_ec, cands = O.stage1(rd, k, m, mercy)
+        got_solid = np.zeros(len(exp_solid) + 8, dtype=np.uint8)
+        got_ec = np.zeros(65536, dtype=np.int64)
+        assert lib_stage1_edges(logic, rd, k, m, got_solid, got_ec) == 0
+        assert np.array_equal(got_ec, exp_ec)
+        assert np.array_equal(got_solid[:len(exp_solid)], exp_solid)
+        if mercy:
+            O.mercy(rd, k, exp_solid, cands)
+    exp = O.stage2(rd, k, m, exp_solid)
+    # general mode: re-count under the (possibly mercy-extended) is_solid filter
+    stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=False)
+    assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
+    if not mercy:
+        # fused mode: multiplicities straight from the stage-1 counts
+        stream, meta, totals = run_edges(logic, rd, k, m, None, fused=True)
+        assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
+
+
+def lib_stage1_edges(lib, rd, k, m, solid, ec):
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
+    return lib.logic_stage1_edges(_p(rd["seq"]), _p(rd["start"]), n, ns, rd["max_len"], k, m, _p(solid), _p(ec))
