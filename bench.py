@@ -195,10 +195,25 @@ def main():
             dist.broadcast(torch.as_tensor(DevBuf(tp, tb), device=dev), 0)
         return h2d
 
-    def merge_solid():
-        if world > 1 and a.m > 1:
-            p, nb = ctx.solid_device_buffer()
-            dist.all_reduce(torch.as_tensor(DevBuf(p, nb), device=dev), op=dist.ReduceOp.SUM)
+    def exchange_edges():
+        """world > 1: all-gather of the solid-edge rows + all-reduce of the stage-2 prefix histogram."""
+        if world == 1:
+            return
+        ptr, n, w = ctx.edges_local()
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = n
+        dist.all_reduce(counts)
+        counts = [int(x) for x in counts.tolist()]
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        buf_ptr = ctx.edges_reserve(offs[-1], offs[rank])
+        buf = torch.as_tensor(DevBuf(buf_ptr, max(offs[-1], 1) * w * 4), device=dev)
+        for j in range(world):
+            if counts[j]:
+                dist.broadcast(buf[offs[j] * w:offs[j + 1] * w], j)
+        hp, hb = ctx.edge_hist_device_buffer()
+        dist.all_reduce(torch.as_tensor(DevBuf(hp, hb), device=dev), op=dist.ReduceOp.SUM)
 
     def step(e2e):
         """-> (edges of this shard, h2d bytes, d2h bytes)"""
@@ -206,7 +221,7 @@ def main():
         d2h = 0
         if a.m > 1:
             ctx.stage1()
-            merge_solid()
+            exchange_edges()
         if e2e:
             nbytes, meta, totals = ctx.stage2(collect="count")
             d2h = nbytes + meta[slice(*ctx.shard_range())].nbytes
@@ -249,6 +264,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # the reference's own stage-2 item count (its lv1 histogram), for the SURVEY-model figure; outside every timed region
+    ref_s2_items = 0
+    if world == 1:
+        try:
+            ref_s2_items = int(ctx.histogram(2).sum())
+        except Exception:
+            ref_s2_items = 0
     edges = total(outs[-1][0])
     h2d = total(outs_e2e[-1][1])
     d2h = total(outs_e2e[-1][2])
@@ -263,25 +285,40 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # per-kernel algorithmic bytes: each kernel reads and writes every byte it must, once
+        # per-kernel algorithmic bytes: what each kernel must read + write once
         seq_bytes = n_words * 4
         kern = []
-        for sname, st in (("s1", st1), ("s2", st2)):
-            n, iw = st["n_items"], st["item_words"]
-            if not n:
-                continue
-            kern.append((sname + ".hist(k_walk)", st["ms_hist"], seq_bytes + 65536 * 8))
-            kern.append((sname + ".extract(k_walk)", st["ms_extract"], seq_bytes * max(1, st["n_batches"]) + n * iw * 4))
-            if st["ms_partition"] > 0:
-                kern.append((sname + ".partition(k_msd)", st["ms_partition"], n * (4 + 2 * iw * 4)))
-            kern.append((sname + ".sort_emit(k_chunk)", st["ms_sort_emit"], n * iw * 4 + st["out_bytes"]))
+        n1, iw1, rows = st1["n_items"], st1["item_words"], st1["n_edges"]
+        row_bytes = (st1["key_words"] + 1) * 4
+        if n1:
+            kern.append(("s1.k_edge_part", st1["ms_extract"], seq_bytes * max(1, st1["n_batches"]) + n1 * iw1 * 4))
+            kern.append(("s1.k_split", st1["ms_partition"], 2 * n1 * iw1 * 4))
+            kern.append(("s1.k_count", st1["ms_sort_emit"], n1 * iw1 * 4 + rows * row_bytes))
+        n2, iw2 = st2["n_items"], st2["item_words"]
+        if n2:
+            kern.append(("s2.k_item_part", st2["ms_extract"], rows * row_bytes * max(1, st2["n_batches"]) + n2 * iw2 * 4))
+            kern.append(("s2.k_split", st2["ms_partition"], 2 * n2 * iw2 * 4))
+            kern.append(("s2.k_chunk", st2["ms_sort_emit"], n2 * iw2 * 4 + st2["out_bytes"]))
         kern.sort(key=lambda x: -x[1])
         top = kern[0]
         ach = top[2] / (top[1] / 1000.0) / 1e9 if top[1] > 0 else 0.0
+        step_bytes = sum(k[2] for k in kern)
         roofline = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": pk_src, "algorithmic_bytes_per_launch": top[2],
+                    "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_dev / 1000.0) / 1e9 / peak / n_gpus,
                     "kernels": [{"name": k[0], "ms": k[1], "bytes": k[2], "gbs": (k[2] / (k[1] / 1000.0) / 1e9 if k[1] > 0 else 0.0)}
                                 for k in kern]}
+        # SURVEY 8(d) model: bytes an 8-bit LSD over all key bits below the bucket prefix would move for the REFERENCE's
+        # item counts (320 B / 192 B per item at k=31); reported beside the honest per-kernel figure, never instead of it
+        def model_bytes_per_item(stage):
+            W = -(-(2 * (a.k - 1) + 6) // 32) if stage == 1 else -(-(2 * a.k + 4) // 32)
+            bits = 2 * (a.k - 1) + 6 if stage == 1 else 2 * a.k + 4
+            P = -(-(bits - 16) // 8)
+            return (4 * W + (8 if stage == 1 else 0)) * (2 + 2 * P)
+        ref_i1 = n_reads * (L - a.k + 4) if a.m > 1 else 0
+        roofline["model"] = {"s1_items_ref": ref_i1, "s2_items_ref": ref_s2_items, "bytes_per_item": [model_bytes_per_item(1), model_bytes_per_item(2)],
+                             "frac": ((ref_i1 * model_bytes_per_item(1) + ref_s2_items * model_bytes_per_item(2)) / (ms_dev / 1000.0) / 1e9 / peak / n_gpus)
+                             if ref_s2_items else None}
         # bytes the reference's LSD model would move per item vs what the kernels above move
         cpu_baseline = None
         if n_gpus == 1 and not a.no_cpu_baseline:

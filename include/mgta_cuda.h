@@ -123,6 +123,18 @@ int mgta_solid_device_buffer(mgta_ctx *ctx, void **dev_ptr, uint64_t *n_bytes);
 int mgta_get_is_solid(mgta_ctx *ctx, uint8_t *host, uint64_t n_bytes);
 int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_bytes);
 
+/* Edge-centric exchange step when world > 1 (replaces the is_solid merge on the hot path): stage 1 of shard r
+ * counts the canonical (k+1)-mers whose hash falls in r's range and leaves its solid edges as rows
+ * {edge words..., multiplicity} on the device.  Every shard needs ALL rows for stage 2:
+ *   1. mgta_edges_local() on every shard -> n_r rows;   all-gather the n_r
+ *   2. mgta_edges_reserve(total, offset_r) -> one buffer of `total` rows with the local rows at offset_r
+ *   3. the caller fills rows [offset_j, offset_j + n_j) from shard j (ncclBroadcast / all-gather over NVLink)
+ *   4. all-reduce SUM (as int32 words) over mgta_edge_hist_device_buffer() -- the stage-2 item histogram by key prefix
+ * then mgta_stage2() emits this shard's lv1-bucket range.  With world == 1 none of this is needed. */
+int mgta_edges_local(mgta_ctx *ctx, void **dev, uint64_t *n_rows, int32_t *row_words);
+int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t my_offset_rows, void **dev);
+int mgta_edge_hist_device_buffer(mgta_ctx *ctx, void **dev, uint64_t *n_bytes);
+
 /* Mercy candidates of this shard (s1.cpp:762-826): packed ((start_idx+kmer_offset)<<2)|flag.
  * Valid after mgta_stage1 with need_mercy.  *n receives the count; copies min(*n, cap). */
 int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t cap, uint64_t *n);

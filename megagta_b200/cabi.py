@@ -39,7 +39,8 @@ SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_
 EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_alloc_reads",
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
-           "mgta_get_mercy_candidates", "mgta_stage2", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
+           "mgta_get_mercy_candidates", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
+           "mgta_edge_hist_device_buffer", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version"]
 
 _lib = None
@@ -73,6 +74,11 @@ def load():
         lib.mgta_get_mercy_candidates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                                   ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_stage2.argtypes = [ctypes.c_void_p, SINK, ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_edges_local.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
+                                         ctypes.POINTER(ctypes.c_int32)]
+        lib.mgta_edges_reserve.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
+        lib.mgta_edge_hist_device_buffer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                     ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_shard_range.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
         lib.mgta_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(StageStats)]
         _lib = lib
@@ -190,6 +196,22 @@ class Context:
         totals = np.zeros(10, dtype=np.int64)
         self._check(self.lib.mgta_stage2(self.h, cb, None, _p(totals)), "mgta_stage2")
         return (b"".join(parts) if collect is True else nbytes_total[0]), meta, totals
+
+    def edges_local(self):
+        """-> (device pointer, rows, u32 words per row) of this shard's solid-edge list"""
+        p, n, w = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_int32()
+        self._check(self.lib.mgta_edges_local(self.h, ctypes.byref(p), ctypes.byref(n), ctypes.byref(w)), "mgta_edges_local")
+        return p.value, n.value, w.value
+
+    def edges_reserve(self, n_total, my_offset):
+        p = ctypes.c_void_p()
+        self._check(self.lib.mgta_edges_reserve(self.h, n_total, my_offset, ctypes.byref(p)), "mgta_edges_reserve")
+        return p.value
+
+    def edge_hist_device_buffer(self):
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self.lib.mgta_edge_hist_device_buffer(self.h, ctypes.byref(p), ctypes.byref(n)), "mgta_edge_hist_device_buffer")
+        return p.value, n.value
 
     def shard_range(self):
         a, b = ctypes.c_int32(), ctypes.c_int32()

@@ -481,9 +481,11 @@ struct TileRuns {
         const unsigned idx = perm[cur];
         const unsigned j = next_flag(rflag, cur + 1, e);
         const uint32_t lw = keys[(W - 1) * capi + idx];
+        unsigned long long sum = 0;                        // items carry the multiplicity of their edge (payload word W)
+        for (unsigned t = cur; t < j; ++t) sum += keys[W * capi + perm[t]];
         r.a = ((lw >> 3) & 1) ? (int)((keys[aw * capi + idx] >> ash) & 3) : SENT;
         r.b = (int)(lw & 7);
-        r.cnt = j - cur;
+        r.cnt = sum > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)sum;
         r.item = idx;
         cur = j;
         return true;
@@ -599,11 +601,15 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_chunk(const ChunkParams P) {
                         if ((lw >> 3) & 1) code = 4 + 5 * ((P.src[(uint64_t)P.aw * P.cap + i] >> P.ash) & 3) + b; else code = b;
                     }
                 }
-                const unsigned peers = __match_any_sync(0xFFFFFFFFu, code);
-                if (valid && (peers & ((1u << lane) - 1)) == 0) {
-                    atomicAdd(&s_gcnt[code], (unsigned)__popc(peers));
-                    if (STAGE == 2 && code < 4)
-                        for (int w = 0; w < P.wpt; ++w) s_glabel[w * 4 + code] = P.src[(uint64_t)w * P.cap + i];
+                if (STAGE == 2) {
+                    if (valid) {
+                        atomicAdd(&s_gcnt[code], P.src[(uint64_t)P.W * P.cap + i]);
+                        if (code < 4)
+                            for (int w = 0; w < P.wpt; ++w) s_glabel[w * 4 + code] = P.src[(uint64_t)w * P.cap + i];
+                    }
+                } else {
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, code);
+                    if (valid && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_gcnt[code], (unsigned)__popc(peers));
                 }
             }
             __syncthreads();

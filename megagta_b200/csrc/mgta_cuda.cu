@@ -17,6 +17,7 @@
 
 #include "../../include/mgta_cuda.h"
 #include "kernels.cuh"
+#include "v2_kernels.cuh"
 
 using namespace mgta;
 
@@ -24,7 +25,8 @@ namespace {
 
 std::string g_create_error;
 
-enum { CTR_TICKET = 0, CTR_NLIST0 = 1, CTR_NLIST1 = 2, CTR_NGIANTS = 3, CTR_ERR = 4, CTR_COUNT = 8 };
+enum { CTR_TICKET = 0, CTR_NLIST0 = 1, CTR_NLIST1 = 2, CTR_NGIANTS = 3, CTR_ERR = 4, CTR_TICKET2 = 5, CTR_TICKET3 = 6, CTR_NOVF = 7,
+       CTR_NOVF2 = 8, CTR_COUNT = 12 };
 enum { PH_HIST = 0, PH_EXTRACT = 1, PH_PARTITION = 2, PH_SORT = 3, PH_COUNT = 4 };
 
 struct Timed {
@@ -62,6 +64,18 @@ struct mgta_ctx {
     mgta_stage_stats stats[2];
     std::vector<Timed> timed;
     uint64_t n_dollar = 0;                 // stage-2 items with a == $ (from the last stage-2 histogram)
+    // edge-centric state: {(canonical (k+1)-mer, multiplicity)} rows of edge_row_words u32, and the histogram of the
+    // stage-2 items they generate by PB-bit key prefix
+    uint32_t *d_edges = nullptr;
+    uint64_t n_edges = 0, edges_cap = 0;
+    int edge_row_words = 0;
+    bool edges_valid = false;
+    bool solid_valid = false;              // d_solid holds the is_solid vector of the last stage 1 (derived on demand)
+    bool stage1_done = false;
+    uint32_t *d_hist_s2 = nullptr;
+    int PB = 20;                           // prefix bits of a stage-2 tile: min(20, 2(k-1)), >= 16
+    uint64_t n_positions = 0;              // edge offsets over all reads
+    bool n_positions_valid = false;
 };
 
 #define CK(call)                                                                                         \
@@ -128,7 +142,7 @@ void make_plan(Plan &pl, int stage, int k, int cap_override) {
     pl.stage = stage;
     pl.k = k;
     pl.W = stage == 1 ? key_words_s1(k) : key_words_s2(k);
-    pl.IW = pl.W + (stage == 1 ? 2 : 0);
+    pl.IW = pl.W + (stage == 1 ? 2 : 1);       // stage 2: key + multiplicity of the generating edge
     // on-chip tile: two CTAs per SM (<= ~112 KB dynamic shared memory each)
     unsigned capi = 8192;
     while (capi > 512 && chunk_smem_bytes(pl.IW, capi) > 112 * 1024) capi -= 512;
@@ -188,7 +202,7 @@ size_t carve(Plan &pl, uint64_t cap, uint64_t n_dollar) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int mgta_abi_version(void) { return 1; }
+extern "C" int mgta_abi_version(void) { return 2; }
 
 extern "C" int mgta_words_per_key(int stage, int kmer_k) { return stage == 1 ? key_words_s1(kmer_k) : key_words_s2(kmer_k); }
 
@@ -230,6 +244,8 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_totals, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ec, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ctr, CTR_COUNT * 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    ctx->PB = std::min(20, 2 * (opts->kmer_k - 1));
+    if ((e = cudaMalloc(&ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     *out = ctx;
     return MGTA_OK;
@@ -241,7 +257,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
-    cudaFree(ctx->d_ctr); cudaFree(ctx->arena);
+    cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -268,6 +284,10 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
     ctx->n_words = n_words; ctx->n_reads = n_reads; ctx->n_short = n_short; ctx->total_bases = total;
     ctx->max_len = max_len;
+    ctx->edges_valid = false;
+    ctx->solid_valid = false;
+    ctx->stage1_done = false;
+    ctx->n_positions_valid = false;
     return MGTA_OK;
 }
 }  // namespace
@@ -328,6 +348,8 @@ int end_timed(mgta_ctx *ctx) {
     return MGTA_OK;
 }
 
+void set_shard_range(mgta_ctx *ctx, uint64_t total);
+
 int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     CK(cudaSetDevice(ctx->opt.device));
@@ -350,7 +372,12 @@ int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     ctx->hist.assign(NUM_BUCKETS, 0);
     uint64_t total = 0;
     for (int b = 0; b < NUM_BUCKETS; ++b) { ctx->hist[b] = (int64_t)ctx->h_pin[b]; total += ctx->h_pin[b]; }
-    // shard = contiguous bucket range balanced by item count
+    set_shard_range(ctx, total);
+    return MGTA_OK;
+}
+
+// shard = contiguous bucket range balanced by item count, from ctx->hist
+void set_shard_range(mgta_ctx *ctx, uint64_t total) {
     auto boundary = [&](int r) {
         if (r <= 0) return 0;
         if (r >= ctx->opt.world) return (int)NUM_BUCKETS;
@@ -364,7 +391,6 @@ int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     };
     ctx->shard_lo = boundary(ctx->opt.rank);
     ctx->shard_hi = boundary(ctx->opt.rank + 1);
-    return MGTA_OK;
 }
 
 int finish_timing(mgta_ctx *ctx, mgta_stage_stats *st) {
@@ -385,22 +411,398 @@ int finish_timing(mgta_ctx *ctx, mgta_stage_stats *st) {
     return MGTA_OK;
 }
 
-// One stage over this context's bucket shard.
-int run_stage(mgta_ctx *ctx, int stage, int64_t *edge_counting, mgta_bucket_sink sink, void *user, int64_t *totals) {
-    mgta_stage_stats *st = &ctx->stats[stage - 1];
-    memset(st, 0, sizeof(*st));
-    cudaEvent_t ev0, ev1;
-    CK(cudaSetDevice(ctx->opt.device));
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
-    CK(cudaEventRecord(ev0, ctx->stream));
-    int rc = histogram(ctx, stage, st);
+// ---- small helpers -------------------------------------------------------------------------------
+struct Carver {
+    size_t o = 0;
+    size_t take(size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; }
+};
+
+int ensure_arena(mgta_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->arena_bytes) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->arena);
+        ctx->arena = nullptr; ctx->arena_bytes = 0;
+        CK(cudaMalloc(&ctx->arena, bytes));
+        ctx->arena_bytes = bytes;
+    }
+    return MGTA_OK;
+}
+
+size_t hbm_budget(mgta_ctx *ctx) {
+    if (ctx->opt.hbm_budget_bytes > 0) return (size_t)ctx->opt.hbm_budget_bytes;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    return (size_t)(0.9 * (double)(free_b + ctx->arena_bytes));
+}
+
+int count_positions(mgta_ctx *ctx) {
+    if (ctx->n_positions_valid) return MGTA_OK;
+    CK(cudaMemsetAsync(ctx->d_totals + 13, 0, 8, ctx->stream));
+    k_count_positions<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_reads, ctx->opt.kmer_k,
+                                                                                     ctx->d_totals + 13);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 13, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_positions = ctx->h_pin[0];
+    ctx->n_positions_valid = true;
+    return MGTA_OK;
+}
+
+#define WE_SWITCH(WE, ...)                                         \
+    switch (WE) {                                                  \
+        case 1: { constexpr int EE = 1; __VA_ARGS__; } break;      \
+        case 2: { constexpr int EE = 2; __VA_ARGS__; } break;      \
+        case 3: { constexpr int EE = 3; __VA_ARGS__; } break;      \
+        case 4: { constexpr int EE = 4; __VA_ARGS__; } break;      \
+        case 5: { constexpr int EE = 5; __VA_ARGS__; } break;      \
+        case 6: { constexpr int EE = 6; __VA_ARGS__; } break;      \
+        case 7: { constexpr int EE = 7; __VA_ARGS__; } break;      \
+        case 8: { constexpr int EE = 8; __VA_ARGS__; } break;      \
+        default: break;                                            \
+    }
+
+template <int PW, int TP>
+int launch_edge_part_t(int WE, const EdgePartParams &P, unsigned grid, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    WE_SWITCH(WE, {
+        const size_t smem = bin_smem_bytes(EE + PW, TP);
+        e = cudaFuncSetAttribute(k_edge_part<EE, PW, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k_edge_part<EE, PW, TP><<<grid, PART_THREADS, smem, st>>>(P);
+    });
+    return e == cudaSuccess ? 0 : -1;
+}
+
+int edge_tile_positions(int IW) { return IW <= 3 ? 4096 : (IW <= 6 ? 2048 : 1024); }
+
+int launch_edge_part(int WE, int PW, const EdgePartParams &P, uint64_t total_bases, cudaStream_t st) {
+    const int TP = edge_tile_positions(WE + PW);
+    const unsigned grid = (unsigned)((total_bases + TP - 1) / TP);
+#define EP_CASE(PWV)                                                        \
+    if (PW == PWV) {                                                        \
+        if (TP == 4096) return launch_edge_part_t<PWV, 4096>(WE, P, grid, st); \
+        if (TP == 2048) return launch_edge_part_t<PWV, 2048>(WE, P, grid, st); \
+        return launch_edge_part_t<PWV, 1024>(WE, P, grid, st);               \
+    }
+    EP_CASE(0) EP_CASE(1) EP_CASE(2)
+#undef EP_CASE
+    return -1;
+}
+
+int launch_count(int WE, bool plus, const CountParams &P, unsigned grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    WE_SWITCH(WE, {
+        if (plus) {
+            e = cudaFuncSetAttribute(k_count<EE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_count<EE, true><<<grid, COUNT_THREADS, smem, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(k_count<EE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_count<EE, false><<<grid, COUNT_THREADS, smem, st>>>(P);
+        }
+    });
+    return e == cudaSuccess ? 0 : -1;
+}
+
+int launch_item_part(int WE, bool plus, const ItemPartParams &P, unsigned grid, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    WE_SWITCH(WE, {
+        const size_t smem = bin_smem_bytes(EE + (plus ? 1 : 0) + 1, ITEM_EDGES * 6);
+        if (plus) {
+            e = cudaFuncSetAttribute(k_item_part<EE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_item_part<EE, true><<<grid, PART_THREADS, smem, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(k_item_part<EE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_item_part<EE, false><<<grid, PART_THREADS, smem, st>>>(P);
+        }
+    });
+    return e == cudaSuccess ? 0 : -1;
+}
+
+unsigned split_chunk_items(int IW) { return IW <= 4 ? 4096u : (IW <= 9 ? 2048u : 1024u); }
+
+int launch_scans(mgta_ctx *ctx, const ScanParams &SP) {
+    const unsigned B1 = SP.NT >> SP.lb2;
+    k_scan_local<<<B1, 256, 0, ctx->stream>>>(SP);
+    k_scan_top<<<1, 1024, 0, ctx->stream>>>(SP);
+    k_scan_apply<<<(SP.NT + 255) / 256, 256, 0, ctx->stream>>>(SP);
+    CK(cudaGetLastError());
+    return MGTA_OK;
+}
+
+int launch_split(mgta_ctx *ctx, const SplitParams &SP) {
+    const size_t smem = bin_smem_bytes(SP.IW, (int)SP.T);
+    CK(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_split, PART_THREADS, smem));
+    k_split<<<(unsigned)(ctx->sm_count * std::max(1, occ)), PART_THREADS, smem, ctx->stream>>>(SP);
+    CK(cudaGetLastError());
+    return MGTA_OK;
+}
+
+// ---- the counting pipeline ------------------------------------------------------------------------
+// reads -> canonical (k+1)-mer items -> two hash partition levels -> per-tile hash tables.
+//   stage-1 mode : marks is_solid, fills edge_counting, lists edges with count >= m (or assist occurrences)
+//   general mode : counts the occurrences the is_solid vector calls solid (no marking), lists every edge
+// Both leave {(canonical edge, multiplicity)} in ctx->d_edges and the stage-2 key-prefix histogram in d_hist_s2.
+enum CountMode { CM_STAGE1 = 0, CM_GENERAL = 1, CM_MARK = 2 };
+
+int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
+    const bool stage1_mode = mode != CM_GENERAL;                   // counts every occurrence of this shard's hash range
+    const bool mark_mode = mode == CM_MARK;                        // only (re)derives the is_solid vector
+    const int k = ctx->opt.kmer_k;
+    int rc = count_positions(ctx);
     if (rc) return rc;
+    const uint64_t n_pos = ctx->n_positions;
+    const int WE = edge_words(k);
+    const bool plus = key_words_s2(k) > WE;
+    const bool has_assist = stage1_mode && ctx->n_short < ctx->n_reads;
+    // the base position rides along only when it is needed: to mark is_solid, or to tell assist occurrences apart
+    const int PW = (mark_mode || has_assist) ? (ctx->total_bases >= 0xFFFFFFFEull ? 2 : 1) : 0;
+    const int IW = WE + PW;
+    st->key_words = WE; st->item_words = IW;
+
+    if (!mark_mode) {
+        ctx->edges_valid = false;
+        ctx->edge_row_words = WE + 1;
+    }
+    if (n_pos == 0) {
+        if (!mark_mode) {
+            ctx->n_edges = 0;
+            CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
+            if (stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
+            ctx->edges_valid = true;
+        }
+        return MGTA_OK;
+    }
+
+    // per-tile table: sized so that two CTAs share an SM; overflow tiles get the largest table that fits one SM
+    const size_t slot_bytes = 4 * (size_t)(2 + (has_assist ? 1 : 0) + WE) + 2;
+    unsigned tab_cap = 4096, big_cap = 16384;
+    while (tab_cap > 1024 && tab_cap * slot_bytes > 96 * 1024) tab_cap >>= 1;
+    while (big_cap > tab_cap && big_cap * slot_bytes > 200 * 1024) big_cap >>= 1;
+    unsigned tab_limit = tab_cap - 640;                            // COUNT_THREADS inserts may be in flight past the check
+    if (ctx->opt.sort_items_cap > 0) tab_limit = std::min<unsigned>(tab_limit, std::max(8, ctx->opt.sort_items_cap));   // test hook: force the overflow pass
+    // tiles of about tab_cap / 2 items: level-2 fan-out <= 1024, level-1 bins as many as it takes (a batch handles <= 1024)
+    int bits = 2;
+    while (bits < 28 && (n_pos >> bits) > (uint64_t)tab_cap * 6 / 10) ++bits;
+    const unsigned lb2 = (unsigned)std::min(10, bits / 2), lb1 = (unsigned)bits - lb2;
+    const unsigned B1 = 1u << lb1;
+    const unsigned T = split_chunk_items(IW);
+    st->sort_cap = (int)tab_cap;
+
+    const size_t budget = hbm_budget(ctx);
+    double slack = 1.15;
+  for (int attempt = 0;; ++attempt) {          // a level-1 slab overflow restarts the pipeline with slabs sized from what was seen
+    bool retry = false;
+    memset(st, 0, sizeof(*st));
+    st->key_words = WE; st->item_words = IW; st->sort_cap = (int)tab_cap; st->n_giants = (uint64_t)attempt;
+    if (mark_mode) {
+        CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
+    } else {
+        ctx->n_edges = 0;
+        CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
+        if (stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
+    }
+    unsigned n_batches = 1;
+    struct Lay { size_t A, B, hist2, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, ovf, total; uint64_t slab_cap, capA, capB; unsigned bins; } L;
+    // this shard's level-1 hash bins (hash ranges balance the shards without a histogram pass)
+    // (the general mode has no exchange step after it, so there every shard counts the whole hash space)
+    const unsigned r_lo = stage1_mode ? (unsigned)((uint64_t)B1 * ctx->opt.rank / ctx->opt.world) : 0u;
+    const unsigned r_hi = stage1_mode ? (unsigned)((uint64_t)B1 * (ctx->opt.rank + 1) / ctx->opt.world) : B1;
+    if (r_lo >= r_hi) { if (!mark_mode) ctx->edges_valid = true; return MGTA_OK; }
+    unsigned NT = 0;                                               // tiles of one batch
+    auto layout = [&](unsigned nb) {
+        L.bins = (r_hi - r_lo + nb - 1) / nb;
+        NT = L.bins << lb2;
+        L.slab_cap = ((uint64_t)((double)n_pos / B1 * slack) + 1024 + 31) & ~(uint64_t)31;
+        L.capA = L.slab_cap * L.bins;
+        L.capB = std::min<uint64_t>(L.capA, (n_pos + 31) & ~(uint64_t)31);
+        Carver c;
+        L.A = c.take((size_t)IW * L.capA * 4);
+        L.B = c.take((size_t)IW * L.capB * 4);
+        L.hist2 = c.take((size_t)NT * 4); L.loc = c.take((size_t)NT * 4);
+        L.off2 = c.take(((size_t)NT + 1) * 8); L.cur2 = c.take((size_t)NT * 8);
+        L.tot = c.take((B1 + 1) * 8); L.base = c.take((B1 + 1) * 8); L.in_start = c.take((B1 + 1) * 8);
+        L.chunk_pref = c.take((B1 + 1) * 4); L.cur1 = c.take((B1 + 1) * 8);
+        L.ovf = c.take((size_t)NT * 4);
+        L.total = c.o;
+    };
+    n_batches = (r_hi - r_lo + MAX_BINS - 1) / MAX_BINS;
+    layout(n_batches);
+    while (L.total > budget && L.bins > 1) { n_batches *= 2; layout(n_batches); }
+    if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 hash bin (%zu B)", budget, L.total);
+
+    const size_t smem_count = count_smem_bytes(WE, tab_cap, has_assist), smem_big = count_smem_bytes(WE, big_cap, has_assist);
+    int occ = 1;
+    for (unsigned batch = 0; batch < n_batches; ++batch) {
+        const unsigned b_lo = r_lo + batch * L.bins, b_hi = std::min(r_hi, b_lo + L.bins);
+        if (b_lo >= b_hi) break;
+        {
+            if ((rc = ensure_arena(ctx, L.total))) return rc;
+            uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
+            uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+            unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+            unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
+            CK(cudaMemsetAsync(hist2, 0, (size_t)NT * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_totals + 14, 0, 8, ctx->stream));                      // edge rows written by this batch
+            k_init_slab_cursors<<<(b_hi - b_lo + 255) / 256, 256, 0, ctx->stream>>>(cur1, b_hi - b_lo, L.slab_cap);
+            CK(cudaGetLastError());
+            // ---- K1+K2: extraction + level-1 hash partition
+            EdgePartParams EP;
+            memset(&EP, 0, sizeof(EP));
+            EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
+            EP.total_bases = ctx->total_bases; EP.k = k;
+            EP.filter = stage1_mode ? 0 : 1; EP.all_solid = ctx->opt.min_count == 1; EP.solid = ctx->d_solid;
+            EP.sh1 = 32 - (int)lb1; EP.sh2 = 32 - bits; EP.lb2 = lb2; EP.b_lo = b_lo; EP.b_hi = b_hi;
+            EP.cursor1 = cur1; EP.slab_cap = L.slab_cap; EP.hist2 = hist2; EP.dst = bufA; EP.cap = L.capA;
+            EP.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
+            if (launch_edge_part(WE, PW, EP, ctx->total_bases, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            if ((rc = end_timed(ctx))) return rc;
+            st->n_launches++;
+            // ---- exact tile offsets, K3a: level-2 split
+            ScanParams SP;
+            memset(&SP, 0, sizeof(SP));
+            const unsigned NTb = (b_hi - b_lo) << lb2;
+            SP.hist = hist2; SP.NT = NTb; SP.lb2 = lb2; SP.t_lo = 0; SP.t_hi = NTb;
+            SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
+            SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
+            SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
+            SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
+            SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
+            SP.T = T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
+            SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
+            if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
+            if ((rc = launch_scans(ctx, SP))) return rc;
+            SplitParams XP;
+            memset(&XP, 0, sizeof(XP));
+            XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = IW; XP.WE = WE; XP.mode = 0;
+            XP.sh2 = 32 - bits; XP.lb2 = lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
+            XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = T; XP.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = launch_split(ctx, XP))) return rc;
+            if ((rc = end_timed(ctx))) return rc;
+            st->n_launches += 4;
+            // ---- K4: per-tile hash counting (edge rows are staged in buffer A, dead after the split)
+            CountParams CP;
+            memset(&CP, 0, sizeof(CP));
+            CP.src = bufB; CP.cap = L.capB; CP.PW = PW; CP.k = k; CP.off2 = off2; CP.t_lo = SP.t_lo; CP.t_hi = SP.t_hi;
+            CP.ticket = ctx->d_ctr + CTR_TICKET2; CP.tab_cap = tab_cap; CP.tab_limit = tab_limit; CP.m = (unsigned)ctx->opt.min_count;
+            CP.mark = mark_mode ? 1 : 0; CP.threshold = stage1_mode ? 1 : 0; CP.has_assist = has_assist ? 1 : 0;
+            CP.emit = mark_mode ? 0 : 1;
+            CP.solid = ctx->d_solid; CP.edge_counting = (stage1_mode && !mark_mode) ? ctx->d_ec : nullptr;
+            CP.edges_out = bufA; CP.n_edges = ctx->d_totals + 14; CP.edges_cap = (uint64_t)IW * L.capA / (WE + 1);
+            CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
+            CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = NT;
+            CP.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = begin_timed(ctx, PH_SORT))) return rc;
+            {
+                cudaError_t e = cudaSuccess;
+                WE_SWITCH(WE, {
+                    if (plus) {
+                        e = cudaFuncSetAttribute(k_count<EE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
+                        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_count<EE, true>, COUNT_THREADS, smem_count);
+                    } else {
+                        e = cudaFuncSetAttribute(k_count<EE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
+                        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_count<EE, false>, COUNT_THREADS, smem_count);
+                    }
+                });
+                if (e != cudaSuccess) occ = 1;
+                cudaGetLastError();
+            }
+            // the occupancy query needs the smem attribute; launch_count sets it (query again is not worth a sync)
+            if (launch_count(WE, plus, CP, (unsigned)(ctx->sm_count * std::max(1, std::min(occ, 4))), smem_count, ctx->stream))
+                FAIL(MGTA_ERR_CUDA, "k_count launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CountParams CB = CP;                                                             // overflow tiles: one CTA per SM, large table
+            CB.tile_list = CP.ovf_list; CB.n_tile_list = CP.n_ovf; CB.ticket = ctx->d_ctr + CTR_TICKET3;
+            CB.tab_cap = big_cap; CB.tab_limit = big_cap - 1024; CB.ovf_cap = 0; CB.n_ovf = ctx->d_ctr + CTR_NOVF2;
+            if (launch_count(WE, plus, CB, (unsigned)ctx->sm_count, smem_big, ctx->stream))
+                FAIL(MGTA_ERR_CUDA, "k_count (overflow pass) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            if ((rc = end_timed(ctx))) return rc;
+            st->n_launches += 2;
+            // ---- batch epilogue
+            unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+            unsigned long long *h_ne = ctx->h_pin + 2 * NUM_BUCKETS + 8;
+            CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_ne, ctx->d_totals + 14, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_ne + 1, off2 + NTb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const unsigned dev_err = h_ctr[CTR_ERR];
+            if (dev_err & ERR_SLAB_OVERFLOW) {                    // this batch was not counted (k_split / k_count bail out)
+                if (attempt >= 6) FAIL(MGTA_ERR_MEM, "level-1 hash bins overflow their slabs even with %.1fx slack", slack);
+                std::vector<unsigned long long> hc(b_hi - b_lo);   // the cursors kept counting past the slab ends: exact bin sizes
+                CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long mx = 0;
+                for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
+                slack = std::max(slack * 1.5, (double)mx / ((double)n_pos / B1) * 1.05);
+                retry = true;
+                break;
+            }
+            if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (count pipeline, bins [%u,%u))", dev_err, b_lo, b_hi);
+            st->n_items += h_ne[1];
+            st->n_batches++;
+            st->msd_levels = std::max<int>(st->msd_levels, (int)h_ctr[CTR_NOVF]);          // overflow tiles (informational)
+            const uint64_t ne = h_ne[0];
+            if (ne) {
+                const size_t row = (size_t)(WE + 1) * 4;
+                if (ctx->n_edges + ne > ctx->edges_cap) {
+                    const uint64_t ncap = std::max<uint64_t>(ctx->n_edges + ne, n_batches > 1 ? (ctx->n_edges + ne) * (n_batches - batch) / 1 : 0);
+                    uint32_t *nbuf = nullptr;
+                    CK(cudaMalloc(&nbuf, ncap * row));
+                    if (ctx->n_edges) CK(cudaMemcpyAsync(nbuf, ctx->d_edges, ctx->n_edges * row, cudaMemcpyDeviceToDevice, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    cudaFree(ctx->d_edges);
+                    ctx->d_edges = nbuf; ctx->edges_cap = ncap;
+                }
+                CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ctx->d_edges) + ctx->n_edges * row, bufA, ne * row, cudaMemcpyDeviceToDevice, ctx->stream));
+                ctx->n_edges += ne;
+            }
+        }
+    }
+    if (!retry) break;
+  }
+    if (mark_mode) ctx->solid_valid = true; else ctx->edges_valid = true;
+    return MGTA_OK;
+}
+
+// is_solid is derived lazily: the hot path (stage 1 -> edge list -> stage 2) never reads it
+int ensure_solid(mgta_ctx *ctx) {
+    if (ctx->solid_valid || !ctx->stage1_done || ctx->opt.min_count == 1) return MGTA_OK;
+    mgta_stage_stats tmp;
+    int rc = run_count(ctx, CM_MARK, &tmp);
+    if (rc) return rc;
+    mgta_stage_stats dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    return finish_timing(ctx, &dummy);
+}
+
+// ---- the emission pipeline -------------------------------------------------------------------------
+// {(canonical edge, multiplicity)} -> stage-2 items (S a | flags, multiplicity) -> two key-prefix partition levels
+// (exact offsets) -> per-tile on-chip sort + W/last/tip/multiplicity records (k_chunk<2>) -> sink.
+int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, mgta_stage_stats *st) {
+    const int k = ctx->opt.kmer_k;
+    const int WE = edge_words(k);
+    const int W = key_words_s2(k), IW = W + 1;
+    const bool plus = W > WE;
+    const int PB = ctx->PB;
+    const unsigned lb1 = (unsigned)PB / 2, lb2 = (unsigned)PB - lb1, B1 = 1u << lb1, NT = 1u << PB;
+    const unsigned tiles_per_bucket = 1u << (PB - 16);
+    int rc;
+    st->key_words = W; st->item_words = IW;
 
     Plan pl;
-    make_plan(pl, stage, ctx->opt.kmer_k, ctx->opt.sort_items_cap);
-    st->key_words = pl.W; st->item_words = pl.IW; st->sort_cap = (int)pl.CAPI;
+    make_plan(pl, 2, k, ctx->opt.sort_items_cap);
+    st->sort_cap = (int)pl.CAPI;
 
+    // tile histogram -> host: lv1 bucket sizes, shard range, batches
+    std::vector<uint32_t> h2(NT);
+    CK(cudaMemcpyAsync(h2.data(), ctx->d_hist_s2, (size_t)NT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hist.assign(NUM_BUCKETS, 0);
+    uint64_t total = 0;
+    for (unsigned t = 0; t < NT; ++t) { ctx->hist[t >> (PB - 16)] += h2[t]; total += h2[t]; }
+    set_shard_range(ctx, total);
     uint64_t shard_items = 0, max_bucket = 0;
     for (int b = ctx->shard_lo; b < ctx->shard_hi; ++b) {
         shard_items += (uint64_t)ctx->hist[b];
@@ -411,218 +813,215 @@ int run_stage(mgta_ctx *ctx, int stage, int64_t *edge_counting, mgta_bucket_sink
 
     CK(cudaMemsetAsync(ctx->d_meta, 0, NUM_BUCKETS * 3 * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_totals, 0, 10 * 8, ctx->stream));
-    if (stage == 1) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
 
-    // ---- HBM budget -> items per batch
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = ctx->opt.hbm_budget_bytes > 0 ? (size_t)ctx->opt.hbm_budget_bytes : (size_t)(0.9 * (double)(free_b + ctx->arena_bytes));
-    {
-        uint64_t cap = std::max<uint64_t>(shard_items, 1024);
-        while (carve(pl, cap, ctx->n_dollar) > budget) {
-            if (cap <= std::max<uint64_t>(max_bucket, 1024)) break;
-            cap = std::max<uint64_t>(std::max<uint64_t>(max_bucket, 1024), (uint64_t)((double)cap * 0.9));
-        }
-        if (carve(pl, cap, ctx->n_dollar) > budget)
-            FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the largest lv1 bucket (%llu items, need %zu B)", budget,
-                 (unsigned long long)max_bucket, pl.total);
-        if (pl.total > ctx->arena_bytes) {
-            CK(cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->arena);
-            ctx->arena = nullptr; ctx->arena_bytes = 0;
-            CK(cudaMalloc(&ctx->arena, pl.total));
-            ctx->arena_bytes = pl.total;
-        }
-        uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + pl.off_a);
-        uint32_t *bufB = reinterpret_cast<uint32_t *>(ctx->arena + pl.off_b);
-        uint32_t *flags = reinterpret_cast<uint32_t *>(ctx->arena + pl.off_flags);
-        uint32_t *win = reinterpret_cast<uint32_t *>(ctx->arena + pl.off_win);
-        unsigned long long *state = reinterpret_cast<unsigned long long *>(ctx->arena + pl.off_state);
-        Seg *lists[2] = {reinterpret_cast<Seg *>(ctx->arena + pl.off_list0), reinterpret_cast<Seg *>(ctx->arena + pl.off_list1)};
-        Giant *giants = reinterpret_cast<Giant *>(ctx->arena + pl.off_giants);
-        unsigned char *outbuf = ctx->arena + pl.off_out;
+    const size_t budget = hbm_budget(ctx);
+    struct Lay { size_t A, B, flags, win, state, list0, list1, giants, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, out, total; } L;
+    auto layout = [&](uint64_t cap) {
+        carve(pl, cap, cap / 3 + 1);
+        Carver c;
+        L.A = c.take((size_t)IW * pl.cap * 4); L.B = c.take((size_t)IW * pl.cap * 4);
+        L.flags = c.take((pl.cap / 32 + 64) * 4);
+        const uint64_t n_win = pl.cap / pl.C + 2;
+        L.win = c.take(n_win * 4); L.state = c.take(n_win * 8);
+        L.list0 = c.take((size_t)pl.list_cap * sizeof(Seg)); L.list1 = c.take((size_t)pl.list_cap * sizeof(Seg));
+        L.giants = c.take((size_t)pl.giants_cap * sizeof(Giant));
+        L.loc = c.take((size_t)NT * 4); L.off2 = c.take(((size_t)NT + 1) * 8); L.cur2 = c.take((size_t)NT * 8);
+        L.tot = c.take((B1 + 1) * 8); L.base = c.take((B1 + 1) * 8); L.in_start = c.take((B1 + 1) * 8);
+        L.chunk_pref = c.take((B1 + 1) * 4); L.cur1 = c.take((B1 + 1) * 8);
+        L.out = c.take(pl.out_cap);
+        L.total = c.o;
+    };
+    uint64_t cap = std::max<uint64_t>(shard_items, 1024);
+    layout(cap);
+    while (L.total > budget && cap > std::max<uint64_t>(max_bucket, 1024)) {
+        cap = std::max<uint64_t>(std::max<uint64_t>(max_bucket, 1024), (uint64_t)((double)cap * 0.9));
+        layout(cap);
+    }
+    if (L.total > budget)
+        FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the largest lv1 bucket (%llu items, need %zu B)", budget, (unsigned long long)max_bucket, L.total);
+    if ((rc = ensure_arena(ctx, L.total))) return rc;
+    uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
+    uint32_t *flags = reinterpret_cast<uint32_t *>(ctx->arena + L.flags), *win = reinterpret_cast<uint32_t *>(ctx->arena + L.win);
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(ctx->arena + L.state);
+    Seg *lists[2] = {reinterpret_cast<Seg *>(ctx->arena + L.list0), reinterpret_cast<Seg *>(ctx->arena + L.list1)};
+    Giant *giants = reinterpret_cast<Giant *>(ctx->arena + L.giants);
+    unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
+    unsigned char *outbuf = ctx->arena + L.out;
+    const unsigned T = split_chunk_items(IW);
 
-        if (stage == 1) CK(cudaFuncSetAttribute(k_chunk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem));
-        else CK(cudaFuncSetAttribute(k_chunk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem));
-        int occ = 1;
-        if (stage == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chunk<1>, CHUNK_THREADS, pl.chunk_smem));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chunk<2>, CHUNK_THREADS, pl.chunk_smem));
-        occ = std::max(1, occ);
+    CK(cudaFuncSetAttribute(k_chunk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chunk<2>, CHUNK_THREADS, pl.chunk_smem));
+    occ = std::max(1, occ);
 
-        std::vector<int64_t> meta_host;
-        std::vector<Seg> seg_host;
-        int b0 = ctx->shard_lo;
-        while (b0 < ctx->shard_hi) {
-            // ---- batch [b0, b1): greedy prefix of buckets that fits `cap`
-            int b1 = b0;
-            uint64_t n_items = 0, batch_max = 0;
-            while (b1 < ctx->shard_hi && n_items + (uint64_t)ctx->hist[b1] <= pl.cap) {
-                n_items += (uint64_t)ctx->hist[b1];
-                batch_max = std::max<uint64_t>(batch_max, (uint64_t)ctx->hist[b1]);
-                ++b1;
-            }
-            if (b1 == b0) FAIL(MGTA_ERR_MEM, "bucket %d (%lld items) exceeds the batch capacity %llu", b0, (long long)ctx->hist[b0], (unsigned long long)pl.cap);
-            st->n_batches++;
-            if (n_items == 0) {
-                if (stage == 2 && sink) {
-                    meta_host.assign((size_t)(b1 - b0) * 3, 0);
-                    if (sink(user, b0, b1, nullptr, 0, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
-                }
-                b0 = b1;
-                continue;
-            }
-            const unsigned n_windows = (unsigned)((n_items + pl.C - 1) / pl.C);
-            // batch-relative bucket offsets -> device cursors
-            unsigned long long *h_cur = ctx->h_pin + NUM_BUCKETS;
-            {
-                uint64_t acc = 0;
-                for (int b = 0; b < NUM_BUCKETS; ++b) {
-                    h_cur[b] = acc;
-                    if (b >= b0 && b < b1) acc += (uint64_t)ctx->hist[b];
-                }
-            }
-            CK(cudaMemcpyAsync(ctx->d_cursor, h_cur, NUM_BUCKETS * 8, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemsetAsync(flags, 0, (n_items / 32 + 64) * 4, ctx->stream));
-            CK(cudaMemsetAsync(win, 0, ((size_t)n_windows + 2) * 4, ctx->stream));
-            CK(cudaMemsetAsync(state, 0, ((size_t)n_windows + 2) * 8, ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
-            k_flags_level0<<<(b1 - b0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cursor, ctx->d_hist, b0, b1, flags);
-            CK(cudaGetLastError());
-            st->n_launches++;
-            // ---- extraction + scatter
-            WalkParams WP = walk_params(ctx);
-            WP.dst = bufA; WP.cap = pl.cap; WP.b_lo = b0; WP.b_hi = b1;
-            if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
-            const unsigned wgrid = (unsigned)((ctx->total_bases + WALK_TILE - 1) / WALK_TILE);
-            if (stage == 1) launch_walk<1, MODE_SCATTER>(pl.W, WP, wgrid, ctx->stream);
-            else launch_walk<2, MODE_SCATTER>(pl.W, WP, wgrid, ctx->stream);
-            CK(cudaGetLastError());
-            if ((rc = end_timed(ctx))) return rc;
-            st->n_launches++;
-            // ---- MSD levels when a bucket does not fit the on-chip tile
-            const uint32_t *sorted_src = bufA;
-            int depth_min = 16;
-            if (batch_max > pl.T) {
-                seg_host.clear();
-                uint64_t acc = 0;
-                for (int b = b0; b < b1; ++b) {
-                    const uint64_t c = (uint64_t)ctx->hist[b];
-                    if (c && (!pl.levels.empty() || c > pl.T)) seg_host.push_back(Seg{acc, (unsigned)c, 0});
-                    acc += c;
-                }
-                // the H2D below reads seg_host asynchronously from pageable memory: CUDA stages it before returning
-                CK(cudaMemcpyAsync(lists[0], seg_host.data(), seg_host.size() * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
-                const unsigned n0 = (unsigned)seg_host.size();
-                CK(cudaMemcpyAsync(ctx->d_ctr + CTR_NLIST0, &n0, 4, cudaMemcpyHostToDevice, ctx->stream));
-                if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
-                if (pl.levels.empty()) {
-                    k_register_giants<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(lists[0], n0, pl.C, giants, ctx->d_ctr + CTR_NGIANTS,
-                                                                              pl.giants_cap, win, ctx->d_ctr + CTR_ERR);
-                    CK(cudaGetLastError());
-                    st->n_launches++;
-                } else {
-                    for (size_t l = 0; l < pl.levels.size(); ++l) {
-                        MsdParams MP;
-                        memset(&MP, 0, sizeof(MP));
-                        MP.src = l == 0 ? bufA : bufB;
-                        MP.dst = l == 0 ? bufB : bufA;
-                        MP.cap = pl.cap; MP.IW = pl.IW;
-                        MP.list = lists[l & 1]; MP.n_list = ctx->d_ctr + CTR_NLIST0 + (l & 1);
-                        MP.word = pl.levels[l].first >> 5;
-                        MP.shift = 32 - (pl.levels[l].first & 31) - pl.levels[l].second;
-                        MP.bins = 1 << pl.levels[l].second;
-                        MP.flags = flags;
-                        MP.next_list = lists[(l + 1) & 1]; MP.next_count = ctx->d_ctr + CTR_NLIST0 + ((l + 1) & 1);
-                        MP.next_cap = pl.list_cap;
-                        MP.last_level = l + 1 == pl.levels.size();
-                        MP.copy_back = l > 0;
-                        MP.T = pl.T; MP.C = pl.C;
-                        MP.giants = giants; MP.n_giants = ctx->d_ctr + CTR_NGIANTS; MP.giants_cap = pl.giants_cap;
-                        MP.win_giant = win; MP.err = ctx->d_ctr + CTR_ERR;
-                        CK(cudaMemsetAsync(ctx->d_ctr + CTR_NLIST0 + ((l + 1) & 1), 0, 4, ctx->stream));
-                        const unsigned grid = l == 0 ? std::min<unsigned>(std::max(1u, n0), (unsigned)ctx->sm_count * 8) : (unsigned)ctx->sm_count * 4;
-                        k_msd<<<grid, MSD_THREADS, 0, ctx->stream>>>(MP);
-                        CK(cudaGetLastError());
-                        st->n_launches++;
-                        st->msd_levels = std::max<int>(st->msd_levels, (int)l + 1);
-                    }
-                    sorted_src = bufB;
-                    depth_min = 16 + pl.levels[0].second;
-                }
-                if ((rc = end_timed(ctx))) return rc;
-            }
-            // ---- on-chip sort + count / emit
-            ChunkParams CP;
-            memset(&CP, 0, sizeof(CP));
-            CP.src = sorted_src; CP.cap = pl.cap; CP.n_items = n_items; CP.W = pl.W; CP.IW = pl.IW; CP.k = pl.k;
-            CP.CAPI = pl.CAPI; CP.C = pl.C; CP.n_windows = n_windows; CP.ticket = ctx->d_ctr + CTR_TICKET;
-            CP.flags = flags; CP.win_giant = win; CP.giants = giants; CP.depth_min = depth_min;
-            CP.n_pass = pl.n_pass;
-            memcpy(CP.pass_lsb, pl.pass_lsb, sizeof(CP.pass_lsb));
-            memcpy(CP.pass_nb, pl.pass_nb, sizeof(CP.pass_nb));
-            CP.g_full = (pl.k - 1) / 16;
-            CP.g_rem_shift = (pl.k - 1) % 16 ? (16 - (pl.k - 1) % 16) * 2 : 32;
-            CP.solid = ctx->d_solid; CP.edge_counting = ctx->d_ec; CP.m = (unsigned)ctx->opt.min_count;
-            CP.aw = (pl.k - 1) >> 4; CP.ash = (15 - ((pl.k - 1) & 15)) * 2; CP.wpt = (2 * pl.k + 31) / 32;
-            CP.out = outbuf; CP.out_cap = pl.out_cap; CP.state = state; CP.meta = ctx->d_meta; CP.totals = ctx->d_totals;
-            CP.err = ctx->d_ctr + CTR_ERR;
-            const unsigned cgrid = std::min<unsigned>(n_windows, (unsigned)(ctx->sm_count * occ));
-            if ((rc = begin_timed(ctx, PH_SORT))) return rc;
-            if (stage == 1) k_chunk<1><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP);
-            else k_chunk<2><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP);
-            CK(cudaGetLastError());
-            if ((rc = end_timed(ctx))) return rc;
-            st->n_launches++;
-            // ---- batch epilogue: error flags, giants, output
-            unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
-            unsigned long long *h_state = ctx->h_pin + 2 * NUM_BUCKETS + 8;
-            CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            if (stage == 2) CK(cudaMemcpyAsync(h_state, state + (n_windows - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            st->n_giants += h_ctr[CTR_NGIANTS];
-            const unsigned dev_err = h_ctr[CTR_ERR];
-            if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage %d, buckets [%d,%d))", dev_err, stage, b0, b1);
-            if (stage == 2) {
-                const unsigned long long bytes = *h_state & ((1ull << 62) - 1);
-                st->out_bytes += bytes;
-                if (sink) {
-                    if (bytes > ctx->h_out_bytes) {
-                        cudaFreeHost(ctx->h_out);
-                        ctx->h_out = nullptr; ctx->h_out_bytes = 0;
-                        CK(cudaHostAlloc(&ctx->h_out, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
-                        ctx->h_out_bytes = bytes + bytes / 4 + 4096;
-                    }
-                    meta_host.resize((size_t)(b1 - b0) * 3);
-                    if (bytes) CK(cudaMemcpyAsync(ctx->h_out, outbuf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-                    CK(cudaMemcpyAsync(meta_host.data(), ctx->d_meta + (size_t)b0 * 3, (size_t)(b1 - b0) * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-                    CK(cudaStreamSynchronize(ctx->stream));
-                    if (sink(user, b0, b1, ctx->h_out, bytes, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
-                }
+    std::vector<int64_t> meta_host;
+    std::vector<Seg> seg_host;
+    int b0 = ctx->shard_lo;
+    while (b0 < ctx->shard_hi) {
+        int b1 = b0;
+        uint64_t n_items = 0;
+        while (b1 < ctx->shard_hi && n_items + (uint64_t)ctx->hist[b1] <= pl.cap) { n_items += (uint64_t)ctx->hist[b1]; ++b1; }
+        if (b1 == b0) FAIL(MGTA_ERR_MEM, "bucket %d (%lld items) exceeds the batch capacity %llu", b0, (long long)ctx->hist[b0], (unsigned long long)pl.cap);
+        st->n_batches++;
+        if (n_items == 0) {
+            if (sink) {
+                meta_host.assign((size_t)(b1 - b0) * 3, 0);
+                if (sink(user, b0, b1, nullptr, 0, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
             }
             b0 = b1;
+            continue;
         }
-    }
-    // ---- stage epilogue
-    if (stage == 1 && edge_counting) {
-        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        const unsigned t_lo = (unsigned)b0 * tiles_per_bucket, t_hi = (unsigned)b1 * tiles_per_bucket;
+        const unsigned n_windows = (unsigned)((n_items + pl.C - 1) / pl.C);
+        CK(cudaMemsetAsync(flags, 0, (n_items / 32 + 64) * 4, ctx->stream));
+        CK(cudaMemsetAsync(win, 0, ((size_t)n_windows + 2) * 4, ctx->stream));
+        CK(cudaMemsetAsync(state, 0, ((size_t)n_windows + 2) * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+        // ---- exact offsets of the batch's tiles
+        ScanParams SP;
+        memset(&SP, 0, sizeof(SP));
+        SP.hist = ctx->d_hist_s2; SP.NT = NT; SP.lb2 = lb2; SP.t_lo = t_lo; SP.t_hi = t_hi;
+        SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
+        SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
+        SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
+        SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
+        SP.cursor1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+        SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
+        SP.T = T; SP.slab_cap = 0; SP.b1_lo = 0;
+        SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
+        if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
+        if ((rc = launch_scans(ctx, SP))) return rc;
+        if ((rc = end_timed(ctx))) return rc;
+        // ---- K2': items of the distinct edges, level-1 prefix partition
+        ItemPartParams IP;
+        memset(&IP, 0, sizeof(IP));
+        IP.edges = ctx->d_edges; IP.n_edges = ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
+        IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = B1; IP.dst = bufA; IP.cap = pl.cap;
+        IP.err = ctx->d_ctr + CTR_ERR;
+        if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
+        if (launch_item_part(WE, plus, IP, (unsigned)((ctx->n_edges + ITEM_EDGES - 1) / ITEM_EDGES), ctx->stream))
+            FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CK(cudaGetLastError());
+        if ((rc = end_timed(ctx))) return rc;
+        // ---- K3a: level-2 prefix split, leaf flags, MSD levels for oversize tiles
+        SplitParams XP;
+        memset(&XP, 0, sizeof(XP));
+        XP.src = bufA; XP.dst = bufB; XP.cap_src = pl.cap; XP.cap_dst = pl.cap; XP.IW = IW; XP.WE = W; XP.mode = 1;
+        XP.sh2 = 32 - PB; XP.lb2 = lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
+        XP.B1 = B1; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET2; XP.T = T; XP.err = ctx->d_ctr + CTR_ERR;
+        if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
+        if ((rc = launch_split(ctx, XP))) return rc;
+        k_flags_tiles<<<(t_hi - t_lo + 255) / 256, 256, 0, ctx->stream>>>(off2, t_lo, t_hi, flags);
+        CK(cudaGetLastError());
+        st->n_launches += 6;
+        seg_host.clear();
+        {
+            uint64_t acc = 0;
+            for (unsigned t = t_lo; t < t_hi; ++t) {
+                if (h2[t] > pl.T) seg_host.push_back(Seg{acc, h2[t], 0});
+                acc += h2[t];
+            }
+        }
+        if (!seg_host.empty()) {
+            CK(cudaMemcpyAsync(lists[0], seg_host.data(), seg_host.size() * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+            const unsigned n0 = (unsigned)seg_host.size();
+            CK(cudaMemcpyAsync(ctx->d_ctr + CTR_NLIST0, &n0, 4, cudaMemcpyHostToDevice, ctx->stream));
+            // digit levels over the (k-1)-mer bits below the tile prefix (never split a group)
+            std::vector<std::pair<int, int>> levels;
+            for (int s = PB; s < 2 * (k - 1);) {                  // digits end on byte boundaries: never straddle a key word
+                const int nb = std::min(8 - (s & 7), 2 * (k - 1) - s);
+                levels.push_back({s, nb});
+                s += nb;
+            }
+            if (levels.empty()) {
+                k_register_giants<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(lists[0], n0, pl.C, giants, ctx->d_ctr + CTR_NGIANTS,
+                                                                          pl.giants_cap, win, ctx->d_ctr + CTR_ERR);
+                CK(cudaGetLastError());
+                st->n_launches++;
+            }
+            for (size_t l = 0; l < levels.size(); ++l) {
+                MsdParams MP;
+                memset(&MP, 0, sizeof(MP));
+                MP.src = bufB; MP.dst = bufA; MP.cap = pl.cap; MP.IW = IW;
+                MP.list = lists[l & 1]; MP.n_list = ctx->d_ctr + CTR_NLIST0 + (l & 1);
+                MP.word = levels[l].first >> 5;
+                MP.shift = 32 - (levels[l].first & 31) - levels[l].second;
+                MP.bins = 1 << levels[l].second;
+                MP.flags = flags;
+                MP.next_list = lists[(l + 1) & 1]; MP.next_count = ctx->d_ctr + CTR_NLIST0 + ((l + 1) & 1);
+                MP.next_cap = pl.list_cap;
+                MP.last_level = l + 1 == levels.size();
+                MP.copy_back = 1;
+                MP.T = pl.T; MP.C = pl.C;
+                MP.giants = giants; MP.n_giants = ctx->d_ctr + CTR_NGIANTS; MP.giants_cap = pl.giants_cap;
+                MP.win_giant = win; MP.err = ctx->d_ctr + CTR_ERR;
+                CK(cudaMemsetAsync(ctx->d_ctr + CTR_NLIST0 + ((l + 1) & 1), 0, 4, ctx->stream));
+                k_msd<<<(unsigned)ctx->sm_count * 4, MSD_THREADS, 0, ctx->stream>>>(MP);
+                CK(cudaGetLastError());
+                st->n_launches++;
+                st->msd_levels = std::max<int>(st->msd_levels, (int)l + 1);
+            }
+        }
+        if ((rc = end_timed(ctx))) return rc;
+        // ---- K3b+K5: on-chip sort + record emission
+        ChunkParams CP;
+        memset(&CP, 0, sizeof(CP));
+        CP.src = bufB; CP.cap = pl.cap; CP.n_items = n_items; CP.W = pl.W; CP.IW = pl.IW; CP.k = pl.k;
+        CP.CAPI = pl.CAPI; CP.C = pl.C; CP.n_windows = n_windows; CP.ticket = ctx->d_ctr + CTR_TICKET;
+        CP.flags = flags; CP.win_giant = win; CP.giants = giants; CP.depth_min = std::min(PB, 2 * (k - 1));
+        CP.n_pass = pl.n_pass;
+        memcpy(CP.pass_lsb, pl.pass_lsb, sizeof(CP.pass_lsb));
+        memcpy(CP.pass_nb, pl.pass_nb, sizeof(CP.pass_nb));
+        CP.g_full = (pl.k - 1) / 16;
+        CP.g_rem_shift = (pl.k - 1) % 16 ? (16 - (pl.k - 1) % 16) * 2 : 32;
+        CP.m = (unsigned)ctx->opt.min_count;
+        CP.aw = (pl.k - 1) >> 4; CP.ash = (15 - ((pl.k - 1) & 15)) * 2; CP.wpt = (2 * pl.k + 31) / 32;
+        CP.out = outbuf; CP.out_cap = pl.out_cap; CP.state = state; CP.meta = ctx->d_meta; CP.totals = ctx->d_totals;
+        CP.err = ctx->d_ctr + CTR_ERR;
+        const unsigned cgrid = std::min<unsigned>(n_windows, (unsigned)(ctx->sm_count * occ));
+        if ((rc = begin_timed(ctx, PH_SORT))) return rc;
+        k_chunk<2><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP);
+        CK(cudaGetLastError());
+        if ((rc = end_timed(ctx))) return rc;
+        st->n_launches++;
+        // ---- batch epilogue: error flags, output
+        unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+        unsigned long long *h_state = ctx->h_pin + 2 * NUM_BUCKETS + 8;
+        CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_state, state + (n_windows - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
+        st->n_giants += h_ctr[CTR_NGIANTS];
+        const unsigned dev_err = h_ctr[CTR_ERR];
+        if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage 2, buckets [%d,%d))", dev_err, b0, b1);
+        const unsigned long long bytes = *h_state & ((1ull << 62) - 1);
+        st->out_bytes += bytes;
+        if (sink) {
+            if (bytes > ctx->h_out_bytes) {
+                cudaFreeHost(ctx->h_out);
+                ctx->h_out = nullptr; ctx->h_out_bytes = 0;
+                CK(cudaHostAlloc(&ctx->h_out, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+                ctx->h_out_bytes = bytes + bytes / 4 + 4096;
+            }
+            meta_host.resize((size_t)(b1 - b0) * 3);
+            if (bytes) CK(cudaMemcpyAsync(ctx->h_out, outbuf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(meta_host.data(), ctx->d_meta + (size_t)b0 * 3, (size_t)(b1 - b0) * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (sink(user, b0, b1, ctx->h_out, bytes, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
+        }
+        b0 = b1;
     }
-    if (stage == 2) {
-        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals, 10 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        uint64_t edges = 0;
-        for (int i = 0; i < 9; ++i) edges += ctx->h_pin[i];
-        st->n_edges = edges;
-        if (totals) for (int i = 0; i < 10; ++i) totals[i] = (int64_t)ctx->h_pin[i];
-    }
-    CK(cudaEventRecord(ev1, ctx->stream));
-    CK(cudaEventSynchronize(ev1));
-    CK(cudaEventElapsedTime(&st->ms_total, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    return finish_timing(ctx, st);
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals, 10 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t edges = 0;
+    for (int i = 0; i < 9; ++i) edges += ctx->h_pin[i];
+    st->n_edges = edges;
+    if (totals) for (int i = 0; i < 10; ++i) totals[i] = (int64_t)ctx->h_pin[i];
+    return MGTA_OK;
 }
+
+struct StageTimer {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
 
 }  // namespace
 
@@ -638,13 +1037,35 @@ extern "C" int mgta_stage1_histogram(mgta_ctx *ctx, int64_t *hist) {
 
 extern "C" int mgta_stage2_histogram(mgta_ctx *ctx, int64_t *hist) {
     if (!ctx || !hist) return MGTA_ERR_ARG;
-    int rc = histogram(ctx, 2, nullptr);
+    if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
+    int rc = ensure_solid(ctx);
+    if (rc) return rc;
+    rc = histogram(ctx, 2, nullptr);
     if (rc) return rc;
     memcpy(hist, ctx->hist.data(), NUM_BUCKETS * 8);
     mgta_stage_stats tmp;
     memset(&tmp, 0, sizeof(tmp));
     return finish_timing(ctx, &tmp);
 }
+
+namespace {
+int stage_begin(mgta_ctx *ctx, mgta_stage_stats *st, StageTimer &tm) {
+    memset(st, 0, sizeof(*st));
+    CK(cudaSetDevice(ctx->opt.device));
+    CK(cudaEventCreate(&tm.ev0));
+    CK(cudaEventCreate(&tm.ev1));
+    CK(cudaEventRecord(tm.ev0, ctx->stream));
+    return MGTA_OK;
+}
+int stage_end(mgta_ctx *ctx, mgta_stage_stats *st, StageTimer &tm) {
+    CK(cudaEventRecord(tm.ev1, ctx->stream));
+    CK(cudaEventSynchronize(tm.ev1));
+    CK(cudaEventElapsedTime(&st->ms_total, tm.ev0, tm.ev1));
+    cudaEventDestroy(tm.ev0);
+    cudaEventDestroy(tm.ev1);
+    return finish_timing(ctx, st);
+}
+}  // namespace
 
 extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
     if (!ctx) return MGTA_ERR_ARG;
@@ -655,20 +1076,46 @@ extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
         return MGTA_OK;
     }
     if (ctx->opt.need_mercy) FAIL(MGTA_ERR_ARG, "need_mercy is not implemented on the device yet");
-    CK(cudaSetDevice(ctx->opt.device));
-    CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
-    return run_stage(ctx, 1, edge_counting, nullptr, nullptr, nullptr);
+    mgta_stage_stats *st = &ctx->stats[0];
+    StageTimer tm;
+    int rc = stage_begin(ctx, st, tm);
+    if (rc) return rc;
+    ctx->solid_valid = false;
+    ctx->stage1_done = false;
+    if ((rc = run_count(ctx, CM_STAGE1, st))) return rc;
+    ctx->stage1_done = true;
+    st->n_edges = ctx->n_edges;                                    // distinct solid edges listed for stage 2
+    if (edge_counting) {
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
+    }
+    return stage_end(ctx, st, tm);
 }
 
 extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals) {
     if (!ctx) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
-    return run_stage(ctx, 2, nullptr, sink, user, totals);
+    mgta_stage_stats *st = &ctx->stats[1];
+    StageTimer tm;
+    int rc = stage_begin(ctx, st, tm);
+    if (rc) return rc;
+    if (!ctx->edges_valid) {
+        // no edge list from stage 1 (min_count == 1, or is_solid was set / merged from outside): count the occurrences the
+        // is_solid vector calls solid.  Its kernels are reported in the stage-2 statistics.
+        mgta_stage_stats tmp;
+        memset(&tmp, 0, sizeof(tmp));
+        if ((rc = run_count(ctx, CM_GENERAL, &tmp))) return rc;
+        st->n_launches += tmp.n_launches;
+    }
+    if ((rc = run_emit(ctx, sink, user, totals, st))) return rc;
+    return stage_end(ctx, st, tm);
 }
 
 extern "C" int mgta_solid_device_buffer(mgta_ctx *ctx, void **dev_ptr, uint64_t *n_bytes) {
     if (!ctx || !dev_ptr || !n_bytes) return MGTA_ERR_ARG;
     if (!ctx->d_solid) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
+    { int rc = ensure_solid(ctx); if (rc) return rc; }
     *dev_ptr = ctx->d_solid;
     *n_bytes = ctx->solid_words * 4;
     return MGTA_OK;
@@ -681,6 +1128,7 @@ extern "C" int mgta_get_is_solid(mgta_ctx *ctx, uint8_t *host, uint64_t n_bytes)
     const uint64_t bits = nk1 > 0 ? (uint64_t)nk1 * ctx->n_short : 0;
     if (n_bytes < (bits + 7) / 8) FAIL(MGTA_ERR_ARG, "get_is_solid: buffer too small");
     CK(cudaSetDevice(ctx->opt.device));
+    { int rc = ensure_solid(ctx); if (rc) return rc; }
     const uint64_t words = (bits + 31) / 32 + 1;
     uint32_t *tmp = nullptr;
     CK(cudaMalloc(&tmp, words * 4));
@@ -720,6 +1168,8 @@ extern "C" int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_
     }
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(tmp);
+    ctx->edges_valid = false;
+    ctx->solid_valid = true;
     return MGTA_OK;
 }
 
@@ -728,6 +1178,37 @@ extern "C" int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t
     (void)host; (void)cap;
     *n = 0;
     FAIL(MGTA_ERR_ARG, "need_mercy is not implemented on the device yet");
+}
+
+extern "C" int mgta_edges_local(mgta_ctx *ctx, void **dev, uint64_t *n_rows, int32_t *row_words) {
+    if (!ctx || !dev || !n_rows || !row_words) return MGTA_ERR_ARG;
+    if (!ctx->edges_valid) FAIL(MGTA_ERR_STATE, "no edge list: run mgta_stage1 first");
+    *dev = ctx->d_edges; *n_rows = ctx->n_edges; *row_words = ctx->edge_row_words;
+    return MGTA_OK;
+}
+
+extern "C" int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t my_offset_rows, void **dev) {
+    if (!ctx || !dev) return MGTA_ERR_ARG;
+    if (!ctx->edges_valid) FAIL(MGTA_ERR_STATE, "no edge list: run mgta_stage1 first");
+    if (my_offset_rows + ctx->n_edges > n_rows_total) FAIL(MGTA_ERR_ARG, "edges_reserve: local rows do not fit at that offset");
+    CK(cudaSetDevice(ctx->opt.device));
+    const size_t row = (size_t)ctx->edge_row_words * 4;
+    uint32_t *nbuf = nullptr;
+    CK(cudaMalloc(&nbuf, std::max<size_t>(n_rows_total * row, 256)));
+    if (ctx->n_edges)
+        CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(nbuf) + my_offset_rows * row, ctx->d_edges, ctx->n_edges * row,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_edges);
+    ctx->d_edges = nbuf; ctx->edges_cap = n_rows_total; ctx->n_edges = n_rows_total;
+    *dev = nbuf;
+    return MGTA_OK;
+}
+
+extern "C" int mgta_edge_hist_device_buffer(mgta_ctx *ctx, void **dev, uint64_t *n_bytes) {
+    if (!ctx || !dev || !n_bytes) return MGTA_ERR_ARG;
+    *dev = ctx->d_hist_s2; *n_bytes = ((uint64_t)1 << ctx->PB) * 4;
+    return MGTA_OK;
 }
 
 extern "C" int mgta_shard_range(mgta_ctx *ctx, int32_t *bucket_begin, int32_t *bucket_end) {

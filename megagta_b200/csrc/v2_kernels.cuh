@@ -1,0 +1,684 @@
+// v2_kernels.cuh -- edge-centric sm_100a kernels of the CX1 reads -> SdBG path (DESIGN.md sections 3-5).
+//
+//   k_edge_part   K1+K2  one pass over the 2-bit packed reads: every edge offset yields the canonical
+//                 (k+1)-mer [+ its base position]; items are binned in shared memory by the top bits
+//                 of a hash and leave the CTA as contiguous runs (one global cursor atomic per bin per
+//                 CTA, no per-item global atomics).  Also accumulates the tile histogram.
+//                 Replaces s1_lv0_calc_bucket_size + s1_lv1_fill_offset + s1_extract_subtstr_
+//                 (reference s1.cpp:177-229, 408-596).
+//   k_split       K3a    second partition level: a level-1 bin is cut into its tiles at exact offsets.
+//   k_count       K4     one tile (<= a few thousand items, all keys with equal top hash bits) per CTA
+//                 pass: shared-memory hash table of the distinct canonical edges, multiplicity
+//                 counting, solid marking (s1.cpp:744-760), edge_counting, and the list of solid
+//                 edges with multiplicities that feeds stage 2.  Replaces lv2 sort + s1_lv2_output_.
+//   k_item_part   K2'    stage-2 items (s2.cpp:586-677) generated from the distinct solid edges instead
+//                 of from every read occurrence, binned by key prefix.
+//   scans         exact tile offsets from the tile histograms.
+//
+// Item arrays are SoA: word w of item i lives at buf[w * cap + i].
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace mgta {
+
+constexpr int PART_THREADS = 512;
+constexpr int MAX_BINS = 1024;
+constexpr int COUNT_THREADS = 512;
+constexpr uint32_t TAG_EMPTY = 0u, TAG_LOCK = 0xFFFFFFFFu, TAG_DEAD = 0xFFFFFFFEu;
+enum { ERR_SLAB_OVERFLOW = 16, ERR_EDGE_LIST_FULL = 32, ERR_OVF_LIST_FULL = 64, ERR_TABLE_FULL = 128 };
+
+// two independent 32-bit hashes of a key: `ha` drives the two partition levels (top bits), `hb`
+// the slot and the fingerprint inside a tile's table.
+template <class KeyAt>
+MGTA_HD void edge_hash(KeyAt key_at, int WE, uint32_t &ha, uint32_t &hb) {
+    uint32_t a = 0x9E3779B9u, b = 0x7F4A7C15u;
+    for (int w = 0; w < WE; ++w) {
+        const uint32_t x = key_at(w);
+        a = (a ^ x) * 0x85EBCA6Bu; a ^= a >> 15;
+        b = (b + x) * 0xC2B2AE35u; b ^= b >> 13;
+    }
+    a *= 0x2C1B3C6Du; a ^= a >> 16; a *= 0x297A2D39u; a ^= a >> 15;
+    b *= 0x846CA68Bu; b ^= b >> 16; b *= 0x9E3779B1u; b ^= b >> 14;
+    ha = a; hb = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory binning of one CTA tile of item slots and coalesced scatter of the runs.
+struct BinSmem {
+    uint32_t *stage;              // [IW][P]  item words by slot
+    uint16_t *bin;                // [P]      bin of slot, 0xFFFF = empty slot
+    uint16_t *rank;               // [P]      arrival rank of the slot inside its bin
+    uint16_t *perm;               // [P]      slot at sorted position j
+    uint32_t *cnt;                // [MAX_BINS]
+    uint32_t *lbase;              // [MAX_BINS + 1]
+    unsigned long long *gbase;    // [MAX_BINS]
+    uint32_t *wsum;               // [PART_THREADS / 32]
+};
+
+__host__ __device__ inline size_t bin_smem_bytes(int IW, int P) {
+    return (size_t)IW * P * 4 + 3 * (size_t)P * 2 + MAX_BINS * 4 + (MAX_BINS + 8) * 4 + MAX_BINS * 8 + 64;
+}
+
+__device__ __forceinline__ void bin_smem_carve(BinSmem &S, unsigned char *p, int IW, int P) {
+    S.gbase = reinterpret_cast<unsigned long long *>(p); p += MAX_BINS * 8;
+    S.stage = reinterpret_cast<uint32_t *>(p); p += (size_t)IW * P * 4;
+    S.cnt = reinterpret_cast<uint32_t *>(p); p += MAX_BINS * 4;
+    S.lbase = reinterpret_cast<uint32_t *>(p); p += (MAX_BINS + 8) * 4;
+    S.wsum = reinterpret_cast<uint32_t *>(p); p += 64;
+    S.bin = reinterpret_cast<uint16_t *>(p); p += (size_t)P * 2;
+    S.rank = reinterpret_cast<uint16_t *>(p); p += (size_t)P * 2;
+    S.perm = reinterpret_cast<uint16_t *>(p);
+}
+
+// Precondition: S.cnt / S.bin / S.rank / S.stage filled for slots [0, n_slots), block synchronised.
+// cursor[b]: next free absolute item index of bin b in dst; slab_cap != 0: bin b may only use indices
+// below (b + 1) * slab_cap (optimistic fixed-capacity slabs; overflow is flagged, never written).
+__device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int P, int NB, unsigned long long *cursor,
+                                            uint32_t *dst, uint64_t cap, unsigned long long slab_cap, unsigned *err) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (NB + PART_THREADS - 1) / PART_THREADS;       // <= 4
+    unsigned local[4], c_[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = tid * per + j;
+        const unsigned c = (j < per && b < NB) ? S.cnt[b] : 0u;
+        c_[j] = c; local[j] = sum; sum += c;
+    }
+    unsigned x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) S.wsum[warp] = x;
+    __syncthreads();
+    unsigned add = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PART_THREADS / 32; ++w) {
+        const unsigned s = S.wsum[w];
+        if (w < warp) add += s;
+        total += s;
+    }
+    const unsigned excl = x - sum + add;
+    unsigned long long g_[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g_[j] = c_[j] ? atomicAdd(cursor + (tid * per + j), (unsigned long long)c_[j]) : 0ull;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = tid * per + j;
+        if (j < per && b < NB) { S.lbase[b] = excl + local[j]; S.gbase[b] = g_[j]; }
+    }
+    if (tid == 0) S.lbase[NB] = total;
+    __syncthreads();
+    for (int i = tid; i < n_slots; i += PART_THREADS) {
+        const unsigned b = S.bin[i];
+        if (b != 0xFFFFu) S.perm[S.lbase[b] + S.rank[i]] = (uint16_t)i;
+    }
+    __syncthreads();
+    bool over = false;
+    for (unsigned j = tid; j < total; j += PART_THREADS) {
+        const unsigned i = S.perm[j], b = S.bin[i];
+        const unsigned long long g = S.gbase[b] + (j - S.lbase[b]);
+        if (slab_cap && g >= (unsigned long long)(b + 1) * slab_cap) { over = true; continue; }
+        for (int w = 0; w < IW; ++w) dst[(uint64_t)w * cap + g] = S.stage[w * P + i];
+    }
+    if (over) atomicOr(err, (unsigned)ERR_SLAB_OVERFLOW);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+struct EdgePartParams {
+    const uint32_t *seq;
+    const uint64_t *start;
+    uint64_t n_reads, n_short, total_bases;
+    int k;
+    int filter, all_solid;          // filter: keep only solid occurrences (stage-2 counting from an is_solid vector)
+    const uint32_t *solid;
+    int sh1, sh2;                   // level-1 bin = ha >> sh1 (global id), level-2 bin = (ha >> sh2) & (2^lb2 - 1)
+    unsigned lb2;
+    unsigned b_lo, b_hi;            // level-1 bins of this batch (at most MAX_BINS); tiles are numbered batch-relative
+    unsigned long long *cursor1;    // [b_hi - b_lo] absolute next index in dst, slab b starts at b * slab_cap
+    unsigned long long slab_cap;
+    uint32_t *hist2;                // [(b_hi - b_lo) << lb2]
+    uint32_t *dst;
+    uint64_t cap;
+    unsigned *err;
+};
+
+// PW = payload words: 0 none, 1 = base position (u32), 2 = base position (lo, hi)
+template <int WE, int PW, int TP>
+__global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int IW = WE + PW;
+    constexpr int SW_WORDS = TP / 16 + WALK_BACK_WORDS + 12;
+    __shared__ __align__(16) uint32_t sw[SW_WORDS];
+    __shared__ uint64_t s_r[2];
+    BinSmem S;
+    bin_smem_carve(S, smem_raw, IW, TP);
+    const int tid = threadIdx.x;
+    const int NB = (int)(P.b_hi - P.b_lo);
+    const uint64_t g0 = (uint64_t)blockIdx.x * TP;
+    const uint64_t gend = min(g0 + (uint64_t)TP, P.total_bases);
+    const uint64_t w_lo = (g0 >> 4) >= WALK_BACK_WORDS ? (g0 >> 4) - WALK_BACK_WORDS : 0;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.seq + w_lo);
+        uint4 *dstw = reinterpret_cast<uint4 *>(sw);
+        for (int i = tid; i < SW_WORDS / 4; i += PART_THREADS) dstw[i] = __ldg(src + i);
+    }
+    for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
+    if (tid == 0) s_r[0] = find_read(P.start, 0, P.n_reads - 1, g0);
+    if (tid == 32) s_r[1] = find_read(P.start, 0, P.n_reads - 1, gend - 1);
+    __syncthreads();
+    const uint64_t r_lo = s_r[0], r_hi = s_r[1];
+    const int k = P.k;
+#pragma unroll 1
+    for (int it = 0; it < TP / PART_THREADS; ++it) {
+        const int slot = it * PART_THREADS + tid;
+        const uint64_t g = g0 + (uint64_t)slot;
+        unsigned bin = 0xFFFFu;
+        if (g < gend) {
+            const uint64_t r = find_read(P.start, r_lo, r_hi, g);
+            const uint64_t s = __ldg(P.start + r);
+            const int64_t L = (int64_t)(__ldg(P.start + r + 1) - s);
+            const int64_t p = (int64_t)(g - s);
+            bool ok = L >= k + 1 && p < L - k;
+            const bool assist = r >= P.n_short;
+            if (ok && P.filter) ok = P.all_solid || assist || bit_at(P.solid, g);
+            if (ok) {
+                uint32_t key[WE];
+                canonical_edge<WE>(sw, (uint32_t)(g - 16 * w_lo), k, key);
+                uint32_t ha, hb;
+                edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
+                const unsigned b1 = ha >> P.sh1;
+                if (b1 >= P.b_lo && b1 < P.b_hi) {
+                    bin = b1 - P.b_lo;
+                    atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & ((1u << P.lb2) - 1u))), 1u);
+#pragma unroll
+                    for (int w = 0; w < WE; ++w) S.stage[w * TP + slot] = key[w];
+                    if (PW >= 1) S.stage[WE * TP + slot] = assist ? 0xFFFFFFFFu : (uint32_t)g;
+                    if (PW >= 2) S.stage[(WE + 1) * TP + slot] = assist ? 0xFFFFFFFFu : (uint32_t)(g >> 32);
+                    S.rank[slot] = (uint16_t)atomicAdd(&S.cnt[bin], 1u);
+                }
+            }
+        }
+        S.bin[slot] = (uint16_t)bin;
+    }
+    __syncthreads();
+    bin_scatter(S, TP, IW, TP, NB, P.cursor1, P.dst, P.cap, P.slab_cap, P.err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact offsets from a tile histogram: hist[t] for t in [t_lo, t_hi) (zero outside), NT = B1 << lb2
+struct ScanParams {
+    const uint32_t *hist;
+    unsigned NT, lb2, t_lo, t_hi;
+    uint32_t *loc;                   // [NT] exclusive scan inside the level-1 bin
+    unsigned long long *tot;         // [B1]
+    unsigned long long *base;        // [B1 + 1]
+    unsigned long long *off2;        // [NT + 1]
+    unsigned long long *cursor2;     // [NT]
+    unsigned long long *cursor1;     // [B1]  (exact mode: start of each level-1 bin) may be null
+    unsigned *chunk_pref;            // [B1 + 1] chunks of T items per level-1 bin
+    unsigned T;
+    // slab mode (stage 1): level-1 input regions are slabs; exact mode: they are the bins themselves
+    unsigned long long slab_cap;
+    unsigned b1_lo;                  // first level-1 bin of the batch (slab mode: slab index = b1 - b1_lo)
+    unsigned long long *in_start;    // [B1]
+};
+
+__global__ void __launch_bounds__(256) k_scan_local(const ScanParams P) {
+    __shared__ unsigned s_w[8];
+    const unsigned b1 = blockIdx.x, B2 = 1u << P.lb2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned per = (B2 + 255) / 256;
+    unsigned sum = 0;
+    for (unsigned j = 0; j < per; ++j) {
+        const unsigned b2 = tid * per + j, t = (b1 << P.lb2) + b2;
+        if (b2 < B2 && t >= P.t_lo && t < P.t_hi) sum += P.hist[t];
+    }
+    unsigned x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    unsigned add = 0, total = 0;
+    for (unsigned w = 0; w < 8; ++w) { if (w < warp) add += s_w[w]; total += s_w[w]; }
+    unsigned run = x - sum + add;
+    for (unsigned j = 0; j < per; ++j) {
+        const unsigned b2 = tid * per + j, t = (b1 << P.lb2) + b2;
+        if (b2 < B2) {
+            P.loc[t] = run;
+            if (t >= P.t_lo && t < P.t_hi) run += P.hist[t];
+        }
+    }
+    if (tid == 0) P.tot[b1] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_top(const ScanParams P) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned s_c[32];
+    const unsigned B1 = P.NT >> P.lb2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long v = tid < B1 ? P.tot[tid] : 0ull;
+    const unsigned c = (unsigned)((v + P.T - 1) / P.T);
+    unsigned long long x = v;
+    unsigned xc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        const unsigned yc = __shfl_up_sync(0xFFFFFFFFu, xc, o);
+        if (lane >= (unsigned)o) { x += y; xc += yc; }
+    }
+    if (lane == 31) { s_w[warp] = x; s_c[warp] = xc; }
+    __syncthreads();
+    unsigned long long add = 0, total = 0;
+    unsigned addc = 0, totc = 0;
+    for (unsigned w = 0; w < 32; ++w) {
+        if (w < warp) { add += s_w[w]; addc += s_c[w]; }
+        total += s_w[w]; totc += s_c[w];
+    }
+    if (tid < B1) {
+        const unsigned long long excl = x - v + add;
+        P.base[tid] = excl;
+        P.chunk_pref[tid] = xc - c + addc;
+        if (P.cursor1) P.cursor1[tid] = excl;
+        P.in_start[tid] = P.slab_cap ? (unsigned long long)(tid >= P.b1_lo ? tid - P.b1_lo : 0u) * P.slab_cap : excl;
+    }
+    if (tid == 0) { P.base[B1] = total; P.chunk_pref[B1] = totc; P.off2[P.NT] = total; }
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const ScanParams P) {
+    const unsigned t = blockIdx.x * 256 + threadIdx.x;
+    if (t < P.NT) {
+        const unsigned long long o = P.base[t >> P.lb2] + P.loc[t];
+        P.off2[t] = o;
+        P.cursor2[t] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SplitParams {
+    const uint32_t *src;
+    uint32_t *dst;
+    uint64_t cap_src, cap_dst;
+    int IW, WE;
+    int mode;                            // 0: hash of the WE key words, 1: prefix bits of key word 0
+    int sh2;                             // tile = x >> sh2 (x = ha or key word 0)
+    unsigned lb2;
+    const unsigned long long *in_start;  // [B1]
+    const unsigned long long *in_count;  // [B1]
+    const unsigned *chunk_pref;          // [B1 + 1]
+    unsigned B1;
+    unsigned long long *cursor2;         // [B1 << lb2] absolute into dst
+    unsigned *ticket;
+    unsigned T;
+    unsigned *err;
+};
+
+__global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_job, s_b1;
+    BinSmem S;
+    const int T = (int)P.T, IW = P.IW, tid = threadIdx.x;
+    bin_smem_carve(S, smem_raw, IW, T);
+    const int NB = 1 << P.lb2;
+    const unsigned n_jobs = P.chunk_pref[P.B1];
+    if (*P.err & ERR_SLAB_OVERFLOW) return;
+    while (true) {
+        if (tid == 0) {
+            const unsigned j = atomicAdd(P.ticket, 1u);
+            s_job = j;
+            if (j < n_jobs) {                                   // level-1 bin of chunk j: last b1 with chunk_pref[b1] <= j
+                unsigned lo = 0, hi = P.B1 - 1;
+                while (lo < hi) {
+                    const unsigned mid = (lo + hi + 1) >> 1;
+                    if (P.chunk_pref[mid] <= j) lo = mid; else hi = mid - 1;
+                }
+                s_b1 = lo;
+            }
+        }
+        for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
+        __syncthreads();
+        const unsigned job = s_job;
+        if (job >= n_jobs) break;
+        const unsigned b1 = s_b1;
+        const unsigned long long c0 = (unsigned long long)(job - P.chunk_pref[b1]) * P.T;
+        const unsigned long long cnt1 = P.in_count[b1];
+        const int n = (int)min((unsigned long long)P.T, cnt1 - c0);
+        const unsigned long long s0 = P.in_start[b1] + c0;
+        for (int w = 0; w < IW; ++w) {
+            const uint32_t *s = P.src + (uint64_t)w * P.cap_src + s0;
+            for (int i = tid; i < n; i += PART_THREADS) S.stage[w * T + i] = s[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += PART_THREADS) {
+            uint32_t x;
+            if (P.mode == 0) {
+                uint32_t hb;
+                edge_hash([&](int w) { return S.stage[w * T + i]; }, P.WE, x, hb);
+            } else {
+                x = S.stage[i];
+            }
+            const unsigned b2 = (x >> P.sh2) & (unsigned)(NB - 1);
+            S.bin[i] = (uint16_t)b2;
+            S.rank[i] = (uint16_t)atomicAdd(&S.cnt[b2], 1u);
+        }
+        __syncthreads();
+        bin_scatter(S, n, IW, T, NB, P.cursor2 + ((size_t)b1 << P.lb2), P.dst, P.cap_dst, 0ull, P.err);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct CountParams {
+    const uint32_t *src;
+    uint64_t cap;
+    int PW, k;
+    const unsigned long long *off2;
+    unsigned t_lo, t_hi;              // tiles of this batch
+    const unsigned *tile_list;        // null: all tiles [t_lo, t_hi); else the overflow list of a previous launch
+    const unsigned *n_tile_list;
+    unsigned *ticket;
+    unsigned tab_cap;                 // power of two
+    unsigned tab_limit;               // max distinct keys accepted per tile (< tab_cap)
+    unsigned m;
+    int mark, threshold, has_assist;  // mark: set is_solid bits; threshold: mult = c >= m ? c : assist count (else c)
+    int emit;                         // append solid edges to edges_out and their stage-2 items to hist_s2
+    uint32_t *solid;
+    unsigned long long *edge_counting;
+    uint32_t *edges_out;              // rows of WE + 1 words
+    unsigned long long *n_edges;
+    unsigned long long edges_cap;
+    uint32_t *hist_s2;                // histogram of the stage-2 items of the emitted edges by key prefix
+    int s2_shift;
+    unsigned *ovf_list, *n_ovf, ovf_cap;
+    unsigned *err;
+};
+
+struct CountSmem {
+    uint32_t *tag, *cnt, *acnt, *keys;
+    uint16_t *emit, *list;            // slots to emit; slots claimed for this tile (the only ones that need clearing)
+};
+
+__host__ __device__ inline size_t count_smem_bytes(int WE, unsigned cap, int has_assist) {
+    return (size_t)cap * 4 * (2 + (has_assist ? 1 : 0) + WE) + (size_t)cap * 4;
+}
+
+template <int WE>
+__device__ __forceinline__ unsigned table_find(const CountSmem &S, unsigned cap, const uint32_t (&key)[WE], uint32_t hb) {
+    const unsigned mask = cap - 1;
+    const uint32_t fp = (hb >> 4) + 1u;
+    unsigned slot = hb & mask;
+    const volatile uint32_t *vtag = S.tag;
+    const volatile uint32_t *vkeys = S.keys;
+    while (true) {
+        const uint32_t t = vtag[slot];
+        if (t == fp) {
+            bool eq = true;
+#pragma unroll
+            for (int w = 0; w < WE; ++w) eq = eq && (vkeys[w * cap + slot] == key[w]);
+            if (eq) return slot;
+        } else if (t == TAG_EMPTY) {
+            return 0xFFFFFFFFu;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+
+template <int WE, bool PLUS>
+__global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int W2 = PLUS ? WE + 1 : WE;
+    const unsigned cap = P.tab_cap, mask = cap - 1, tid = threadIdx.x;
+    CountSmem S;
+    {
+        unsigned char *p = smem_raw;
+        S.tag = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4;
+        S.cnt = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4;
+        S.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4 * WE;
+        S.acnt = S.cnt;
+        if (P.has_assist) { S.acnt = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4; }
+        S.emit = reinterpret_cast<uint16_t *>(p); p += (size_t)cap * 2;
+        S.list = reinterpret_cast<uint16_t *>(p);
+    }
+    __shared__ unsigned s_tile2[2], s_ndist, s_sawlock, s_nemit, s_ec[256];
+    __shared__ unsigned long long s_ebase;
+    for (unsigned i = tid; i < 256; i += COUNT_THREADS) s_ec[i] = 0;
+    const unsigned n_tiles = P.tile_list ? *P.n_tile_list : P.t_hi - P.t_lo;
+    volatile uint32_t *vtag = S.tag;
+    volatile uint32_t *vkeys = S.keys;
+    if (*P.err & ERR_SLAB_OVERFLOW) return;                       // the partition is incomplete: the host retries with larger slabs
+    for (unsigned i = tid; i < cap; i += COUNT_THREADS) { S.tag[i] = TAG_EMPTY; S.cnt[i] = 0; }
+    if (P.has_assist) for (unsigned i = tid; i < cap; i += COUNT_THREADS) S.acnt[i] = 0;
+
+    for (unsigned iter = 0;; ++iter) {
+        if (tid == 0) {
+            s_tile2[iter & 1] = atomicAdd(P.ticket, 1u);          // double-buffered: laggards of the previous tile still read theirs
+            s_ndist = 0; s_sawlock = 0; s_nemit = 0;
+        }
+        __syncthreads();                                          // the table is clean here (cleared at the end of every tile)
+        const unsigned s_tile = s_tile2[iter & 1];
+        if (s_tile >= n_tiles) break;
+        const unsigned t = P.tile_list ? P.tile_list[s_tile] : P.t_lo + s_tile;
+        const unsigned long long lo = P.off2[t], hi = P.off2[t + 1];
+        if (hi == lo) continue;                                   // uniform: no divergent barrier
+        // ---- phase A: insert / count
+        for (unsigned long long i = lo + tid; i < hi; i += COUNT_THREADS) {
+            uint32_t key[WE];
+#pragma unroll
+            for (int w = 0; w < WE; ++w) key[w] = P.src[(uint64_t)w * P.cap + i];
+            bool assist = false;
+            if (P.has_assist && P.PW) assist = P.src[(uint64_t)WE * P.cap + i] == 0xFFFFFFFFu &&
+                                                (P.PW < 2 || P.src[(uint64_t)(WE + 1) * P.cap + i] == 0xFFFFFFFFu);
+            uint32_t ha, hb;
+            edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
+            const uint32_t fp = (hb >> 4) + 1u;
+            unsigned slot = hb & mask;
+            bool placed = false;
+            while (!placed) {
+                const uint32_t tg = vtag[slot];
+                if (tg == fp) {
+                    bool eq = true;
+#pragma unroll
+                    for (int w = 0; w < WE; ++w) eq = eq && (vkeys[w * cap + slot] == key[w]);
+                    if (eq) { placed = true; break; }
+                } else if (tg == TAG_EMPTY) {
+                    if (*(volatile unsigned *)&s_ndist >= P.tab_limit) break;   // table full: tile goes to the overflow list
+                    if (atomicCAS(&S.tag[slot], TAG_EMPTY, TAG_LOCK) == TAG_EMPTY) {
+#pragma unroll
+                        for (int w = 0; w < WE; ++w) vkeys[w * cap + slot] = key[w];
+                        __threadfence_block();
+                        vtag[slot] = fp;
+                        S.list[atomicAdd(&s_ndist, 1u)] = (uint16_t)slot;
+                        placed = true;
+                        break;
+                    }
+                    continue;                                     // lost the race: look at the slot again
+                } else if (tg == TAG_LOCK) {
+                    s_sawlock = 1;                                // may create a duplicate entry further on: fixed below
+                }
+                slot = (slot + 1) & mask;
+            }
+            if (placed) {
+                atomicAdd(&S.cnt[slot], 1u);
+                if (assist) atomicAdd(&S.acnt[slot], 1u);
+            }
+        }
+        __syncthreads();
+        const unsigned nd = s_ndist;                              // slots claimed (<= tab_limit + COUNT_THREADS - 1 < cap)
+        if (nd >= P.tab_limit) {                                  // uniform
+            if (tid == 0) {
+                const unsigned o = atomicAdd(P.n_ovf, 1u);
+                if (o < P.ovf_cap) P.ovf_list[o] = t; else atomicOr(P.err, (unsigned)(P.tile_list ? ERR_TABLE_FULL : ERR_OVF_LIST_FULL));
+                if (P.tile_list) atomicOr(P.err, (unsigned)ERR_TABLE_FULL);
+            }
+            for (unsigned i = tid; i < nd; i += COUNT_THREADS) { const unsigned sl = S.list[i]; S.tag[sl] = TAG_EMPTY; S.cnt[sl] = 0; S.acnt[sl] = 0; }
+            __syncthreads();
+            continue;
+        }
+        // ---- duplicates left behind by skipped locked slots: fold into the first entry in probe order
+        if (s_sawlock) {                                          // uniform
+            for (unsigned li = tid; li < nd; li += COUNT_THREADS) {
+                const unsigned s = S.list[li];
+                uint32_t key[WE];
+#pragma unroll
+                for (int w = 0; w < WE; ++w) key[w] = S.keys[w * cap + s];
+                uint32_t ha, hb;
+                edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
+                const unsigned first = table_find<WE>(S, cap, key, hb);
+                if (first != s && first != 0xFFFFFFFFu) {
+                    atomicAdd(&S.cnt[first], S.cnt[s]);
+                    if (P.has_assist) atomicAdd(&S.acnt[first], S.acnt[s]);
+                    vtag[s] = TAG_DEAD;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase B: solid marking of every occurrence
+        if (P.mark) {
+            for (unsigned long long i = lo + tid; i < hi; i += COUNT_THREADS) {
+                const uint32_t p0 = P.src[(uint64_t)WE * P.cap + i];
+                const uint32_t p1 = P.PW >= 2 ? P.src[(uint64_t)(WE + 1) * P.cap + i] : 0u;
+                if (p0 == 0xFFFFFFFFu && (P.PW < 2 || p1 == 0xFFFFFFFFu)) continue;       // assist read: never marked (s1.cpp:757)
+                uint32_t key[WE];
+#pragma unroll
+                for (int w = 0; w < WE; ++w) key[w] = P.src[(uint64_t)w * P.cap + i];
+                uint32_t ha, hb;
+                edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
+                const unsigned slot = table_find<WE>(S, cap, key, hb);
+                if (slot != 0xFFFFFFFFu && S.cnt[slot] >= P.m) {
+                    const unsigned long long g = ((unsigned long long)p1 << 32) | p0;
+                    atomicOr(P.solid + (g >> 5), 1u << (g & 31));
+                }
+            }
+        }
+        // ---- phase C: per distinct edge: edge_counting (s1.cpp:744-746) and the solid edge list
+        for (unsigned li = tid; li < nd; li += COUNT_THREADS) {
+            const unsigned s = S.list[li];
+            if (S.tag[s] == TAG_DEAD) continue;
+            const unsigned c = S.cnt[s];
+            if (P.edge_counting) {
+                if (c < 256) atomicAdd(&s_ec[c], 1u);
+                else atomicAdd(P.edge_counting + (c < 65535u ? c : 65535u), 1ull);
+            }
+            const unsigned mult = P.threshold ? (c >= P.m ? c : (P.has_assist ? S.acnt[s] : 0u)) : c;
+            if (mult && P.emit) S.emit[atomicAdd(&s_nemit, 1u)] = (uint16_t)s;
+        }
+        __syncthreads();
+        const unsigned ne = s_nemit;
+        if (ne) {                                                 // uniform
+            if (tid == 0) {
+                const unsigned long long b = atomicAdd(P.n_edges, (unsigned long long)ne);
+                s_ebase = b;
+                if (b + ne > P.edges_cap) atomicOr(P.err, (unsigned)ERR_EDGE_LIST_FULL);
+            }
+            __syncthreads();
+            const unsigned long long eb = s_ebase;
+            if (eb + ne <= P.edges_cap) {
+                for (unsigned j = tid; j < ne; j += COUNT_THREADS) {
+                    const unsigned s = S.emit[j];
+                    const unsigned c = S.cnt[s];
+                    const unsigned mult = P.threshold ? (c >= P.m ? c : S.acnt[s]) : c;
+                    uint32_t key[WE];
+#pragma unroll
+                    for (int w = 0; w < WE; ++w) key[w] = S.keys[w * cap + s];
+                    uint32_t *row = P.edges_out + (eb + j) * (WE + 1);
+#pragma unroll
+                    for (int w = 0; w < WE; ++w) row[w] = key[w];
+                    row[WE] = mult;
+                    s2_items_of_edge<W2, WE>(key, P.k, [&](const uint32_t(&y)[W2]) { atomicAdd(P.hist_s2 + (y[0] >> P.s2_shift), 1u); });
+                }
+            }
+            __syncthreads();
+        }
+        for (unsigned i = tid; i < nd; i += COUNT_THREADS) { const unsigned sl = S.list[i]; S.tag[sl] = TAG_EMPTY; S.cnt[sl] = 0; S.acnt[sl] = 0; }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (P.edge_counting)
+        for (unsigned i = tid; i < 256; i += COUNT_THREADS)
+            if (s_ec[i]) atomicAdd(P.edge_counting + i, (unsigned long long)s_ec[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ItemPartParams {
+    const uint32_t *edges;            // rows of WE + 1 words
+    unsigned long long n_edges;
+    int k, sh1;                       // level-1 bin = key word 0 >> sh1
+    unsigned bkt_lo, bkt_hi;          // lv1 buckets (top 16 key bits) of this batch
+    unsigned long long *cursor1;      // [B1] exact absolute starts
+    unsigned NB;
+    uint32_t *dst;
+    uint64_t cap;
+    unsigned *err;
+};
+
+constexpr int ITEM_EDGES = 512;       // edges per CTA -> <= 3072 item slots
+
+template <int WE, bool PLUS>
+__global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int W2 = PLUS ? WE + 1 : WE;
+    constexpr int IW = W2 + 1, SLOTS = ITEM_EDGES * 6;
+    BinSmem S;
+    bin_smem_carve(S, smem_raw, IW, SLOTS);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (int)P.NB; i += PART_THREADS) S.cnt[i] = 0;
+    for (int i = tid; i < SLOTS; i += PART_THREADS) S.bin[i] = 0xFFFFu;
+    __syncthreads();
+    const unsigned long long e0 = (unsigned long long)blockIdx.x * ITEM_EDGES;
+    for (int el = tid; el < ITEM_EDGES; el += PART_THREADS) {
+        const unsigned long long e = e0 + el;
+        if (e >= P.n_edges) break;
+        const uint32_t *row = P.edges + e * (WE + 1);
+        uint32_t key[WE];
+#pragma unroll
+        for (int w = 0; w < WE; ++w) key[w] = __ldg(row + w);
+        const uint32_t mult = __ldg(row + WE);
+        int j = 0;
+        s2_items_of_edge<W2, WE>(key, P.k, [&](const uint32_t(&y)[W2]) {
+            const unsigned bkt = y[0] >> 16;
+            if (bkt >= P.bkt_lo && bkt < P.bkt_hi) {
+                const int slot = el * 6 + j;
+                const unsigned b = y[0] >> P.sh1;
+#pragma unroll
+                for (int w = 0; w < W2; ++w) S.stage[w * SLOTS + slot] = y[w];
+                S.stage[W2 * SLOTS + slot] = mult;
+                S.bin[slot] = (uint16_t)b;
+                S.rank[slot] = (uint16_t)atomicAdd(&S.cnt[b], 1u);
+            }
+            ++j;
+        });
+    }
+    __syncthreads();
+    bin_scatter(S, SLOTS, IW, SLOTS, (int)P.NB, P.cursor1, P.dst, P.cap, 0ull, P.err);
+}
+
+// leaf-start flags of the non-empty tiles of a batch (the on-chip sort's windows never straddle a leaf)
+__global__ void k_flags_tiles(const unsigned long long *__restrict__ off2, unsigned t_lo, unsigned t_hi, uint32_t *flags) {
+    const unsigned t = t_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < t_hi) {
+        const unsigned long long s = off2[t];
+        if (off2[t + 1] > s) atomicOr(flags + (s >> 5), 1u << (s & 31));
+    }
+}
+
+// edges * 1: number of edge offsets (k+1)-mer positions over all reads
+__global__ void k_init_slab_cursors(unsigned long long *cursor, unsigned n, unsigned long long slab_cap) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cursor[i] = (unsigned long long)i * slab_cap;
+}
+
+__global__ void k_count_positions(const uint64_t *__restrict__ start, uint64_t n_reads, int k, unsigned long long *out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (r < n_reads) {
+        const int64_t L = (int64_t)(start[r + 1] - start[r]);
+        if (L >= k + 1) v = (unsigned long long)(L - k);
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+}  // namespace mgta

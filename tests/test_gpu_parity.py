@@ -64,15 +64,25 @@ def test_gpu_matches_oracle(read_lib, ds, k, m):
 
 @pytest.mark.parametrize("ds,k,m,cap", [("smoke", 31, 2, 256), ("adversarial", 31, 2, 128), ("adversarial", 21, 1, 64),
                                         ("tiny", 25, 2, 64), ("smoke", 61, 2, 64)])
-def test_gpu_small_tiles_force_msd_levels_and_giants(read_lib, ds, k, m, cap):
-    """A tiny on-chip tile makes every bucket oversize: exercises all MSD levels and the counted giant groups."""
+def test_gpu_small_tables_force_the_overflow_pass(read_lib, ds, k, m, cap):
+    """A tiny per-tile table limit sends every hash tile through the large-table overflow pass of the counting
+    pipeline; a tiny on-chip sort tile makes stage-2 prefix tiles oversize (MSD levels)."""
     _, rd = read_lib(ds)
     got = run_gpu(rd, k, m, sort_items_cap=cap)
     check_vs_oracle(rd, k, m, got)
+    if m > 1 and ds != "tiny":
+        assert got["stats1"]["msd_levels"] >= 1          # overflow tiles of the counting pass
+
+
+def test_gpu_small_sort_tiles_force_msd_levels(golden, read_lib):
+    g = golden["cases"]["meta200k_k31_m2"]
+    _, rd = read_lib(g["dataset"])
+    got = run_gpu(rd, g["k"], g["m"], sort_items_cap=64)
+    check_vs_golden(got, g)
     assert got["stats2"]["msd_levels"] >= 1
 
 
-@pytest.mark.parametrize("ds,k,m,budget", [("smoke", 31, 2, 24 << 20), ("adversarial", 27, 3, 16 << 20)])
+@pytest.mark.parametrize("ds,k,m,budget", [("smoke", 31, 2, 24 << 20), ("adversarial", 27, 3, 24 << 20)])
 def test_gpu_small_hbm_budget_forces_batches(read_lib, ds, k, m, budget):
     _, rd = read_lib(ds)
     got = run_gpu(rd, k, m, hbm_budget_bytes=budget)
@@ -114,6 +124,63 @@ def test_gpu_shards_concatenate_to_the_whole_graph(read_lib):
             totals = np.zeros(10, dtype=np.int64)
             for c in ctxs:
                 c.set_is_solid(solid)
+                st, mt, tt = c.stage2()
+                streams.append(st)
+                meta += mt
+                totals += tt
+            assert b"".join(streams) == whole["stream"]
+            assert np.array_equal(meta, whole["meta"])
+            assert np.array_equal(totals, whole["totals"])
+        finally:
+            for c in ctxs:
+                c.close()
+
+
+def _dev_tensor(ptr, nbytes):
+    import torch
+
+    class _Buf:
+        __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(_Buf(), device="cuda:0")
+
+
+@pytest.mark.parametrize("ds,k,m", [("smoke", 31, 2), ("adversarial", 27, 3), ("meta200k", 61, 2)])
+def test_gpu_edge_exchange_between_shards(read_lib, ds, k, m):
+    """The hot multi-GPU flow on one device: hash-sharded stage 1, all-gather of the solid-edge rows, all-reduce of
+    the stage-2 prefix histogram, bucket-sharded stage 2 (what bench.py does with NCCL)."""
+    import torch
+    _, rd = read_lib(ds)
+    whole = run_gpu(rd, k, m)
+    for world in (2, 5):
+        ctxs = [cabi.Context(k, m, rank=r, world=world) for r in range(world)]
+        try:
+            ec = np.zeros(65536, dtype=np.int64)
+            for c in ctxs:
+                c.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+                ec += c.stage1()
+            assert np.array_equal(ec, whole["counting"])
+            rows = [c.edges_local() for c in ctxs]
+            n = [r[1] for r in rows]
+            w = rows[0][2]
+            offs = np.concatenate([[0], np.cumsum(n)]).astype(int)
+            total = int(offs[-1])
+            parts = [_dev_tensor(r[0], r[1] * w * 4).clone() if r[1] else None for r in rows]
+            hists = []
+            for c in ctxs:
+                p, nb = c.edge_hist_device_buffer()
+                hists.append(_dev_tensor(p, nb))
+            hsum = torch.stack(hists).sum(dim=0, dtype=torch.int32)
+            for r, c in enumerate(ctxs):
+                p = c.edges_reserve(total, int(offs[r]))
+                buf = _dev_tensor(p, max(total, 1) * w * 4)
+                for j in range(world):
+                    if j != r and n[j]:
+                        buf[offs[j] * w:(offs[j] + n[j]) * w] = parts[j]
+                hists[r].copy_(hsum)
+            torch.cuda.synchronize()
+            streams, meta = [], np.zeros((65536, 3), dtype=np.int64)
+            totals = np.zeros(10, dtype=np.int64)
+            for c in ctxs:
                 st, mt, tt = c.stage2()
                 streams.append(st)
                 meta += mt
