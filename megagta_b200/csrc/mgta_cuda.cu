@@ -18,6 +18,7 @@
 #include "../../include/mgta_cuda.h"
 #include "kernels.cuh"
 #include "v2_kernels.cuh"
+#include "emit_kernels.cuh"
 
 using namespace mgta;
 
@@ -143,14 +144,15 @@ void make_plan(Plan &pl, int stage, int k, int cap_override) {
     pl.k = k;
     pl.W = stage == 1 ? key_words_s1(k) : key_words_s2(k);
     pl.IW = pl.W + (stage == 1 ? 2 : 1);       // stage 2: key + multiplicity of the generating edge
-    // on-chip tile: two CTAs per SM (<= ~112 KB dynamic shared memory each)
-    unsigned capi = 8192;
-    while (capi > 512 && chunk_smem_bytes(pl.IW, capi) > 112 * 1024) capi -= 512;
-    if (cap_override > 0) capi = std::max(64, (cap_override / 64) * 64);
+    // on-chip window: two CTAs per SM (<= ~110 KB dynamic shared memory each), at most 4096 items (8 per thread)
+    unsigned capi = 4096;
+    while (capi > 512 && sort_emit_smem_bytes(pl.IW, capi) > 110 * 1024) capi -= 512;
+    if (cap_override > 0) capi = std::min(4096, std::max(128, (cap_override / 64) * 64));   // groups hold <= 48 items: T >= 64
     pl.CAPI = capi;
-    pl.T = capi / 2;
-    pl.C = capi / 2;
-    pl.chunk_smem = chunk_smem_bytes(pl.IW, capi);
+    pl.T = capi / 2;                                               // largest leaf the MSD levels leave alone
+    pl.C = capi / 2;                                               // window stride: C + largest leaf (>= one 48-item group) <= CAPI
+    if (cap_override > 0) pl.T = std::max(16, std::min<int>(cap_override, (int)capi) / 2);
+    pl.chunk_smem = sort_emit_smem_bytes(pl.IW, capi);
     // MSD digit levels over the (k-1)-mer bits below the 16-bit lv1 prefix (never split a group)
     const int GB = 2 * (k - 1);
     pl.levels.clear();
@@ -815,20 +817,21 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     CK(cudaMemsetAsync(ctx->d_totals, 0, 10 * 8, ctx->stream));
 
     const size_t budget = hbm_budget(ctx);
-    struct Lay { size_t A, B, flags, win, state, list0, list1, giants, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, out, total; } L;
+    struct Lay { size_t A, B, flags, win, state, list0, list1, giants, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, out, tmp, total; } L;
     auto layout = [&](uint64_t cap) {
         carve(pl, cap, cap / 3 + 1);
         Carver c;
         L.A = c.take((size_t)IW * pl.cap * 4); L.B = c.take((size_t)IW * pl.cap * 4);
         L.flags = c.take((pl.cap / 32 + 64) * 4);
         const uint64_t n_win = pl.cap / pl.C + 2;
-        L.win = c.take(n_win * 4); L.state = c.take(n_win * 8);
+        L.win = c.take(n_win * 4); L.state = c.take((2 * n_win + 4) * 8);
         L.list0 = c.take((size_t)pl.list_cap * sizeof(Seg)); L.list1 = c.take((size_t)pl.list_cap * sizeof(Seg));
         L.giants = c.take((size_t)pl.giants_cap * sizeof(Giant));
         L.loc = c.take((size_t)NT * 4); L.off2 = c.take(((size_t)NT + 1) * 8); L.cur2 = c.take((size_t)NT * 8);
         L.tot = c.take((B1 + 1) * 8); L.base = c.take((B1 + 1) * 8); L.in_start = c.take((B1 + 1) * 8);
         L.chunk_pref = c.take((B1 + 1) * 4); L.cur1 = c.take((B1 + 1) * 8);
         L.out = c.take(pl.out_cap);
+        L.tmp = c.take(pl.out_cap);
         L.total = c.o;
     };
     uint64_t cap = std::max<uint64_t>(shard_items, 1024);
@@ -846,12 +849,18 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     Seg *lists[2] = {reinterpret_cast<Seg *>(ctx->arena + L.list0), reinterpret_cast<Seg *>(ctx->arena + L.list1)};
     Giant *giants = reinterpret_cast<Giant *>(ctx->arena + L.giants);
     unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
-    unsigned char *outbuf = ctx->arena + L.out;
+    unsigned char *outbuf = ctx->arena + L.out, *tmpbuf = ctx->arena + L.tmp;
     const unsigned T = split_chunk_items(IW);
 
-    CK(cudaFuncSetAttribute(k_chunk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem));
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chunk<2>, CHUNK_THREADS, pl.chunk_smem));
+    {
+        cudaError_t e = cudaSuccess;
+        W_SWITCH(W, {
+            e = cudaFuncSetAttribute(k_sort_emit<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sort_emit<WW>, CHUNK_THREADS, pl.chunk_smem);
+        });
+        if (e != cudaSuccess) FAIL(MGTA_ERR_CUDA, "k_sort_emit setup failed: %s", cudaGetErrorString(e));
+    }
     occ = std::max(1, occ);
 
     std::vector<int64_t> meta_host;
@@ -875,7 +884,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         const unsigned n_windows = (unsigned)((n_items + pl.C - 1) / pl.C);
         CK(cudaMemsetAsync(flags, 0, (n_items / 32 + 64) * 4, ctx->stream));
         CK(cudaMemsetAsync(win, 0, ((size_t)n_windows + 2) * 4, ctx->stream));
-        CK(cudaMemsetAsync(state, 0, ((size_t)n_windows + 2) * 8, ctx->stream));
+        CK(cudaMemsetAsync(state, 0, (2 * (size_t)n_windows + 4) * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
         // ---- exact offsets of the batch's tiles
         ScanParams SP;
@@ -976,24 +985,27 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         CP.g_rem_shift = (pl.k - 1) % 16 ? (16 - (pl.k - 1) % 16) * 2 : 32;
         CP.m = (unsigned)ctx->opt.min_count;
         CP.aw = (pl.k - 1) >> 4; CP.ash = (15 - ((pl.k - 1) & 15)) * 2; CP.wpt = (2 * pl.k + 31) / 32;
-        CP.out = outbuf; CP.out_cap = pl.out_cap; CP.state = state; CP.meta = ctx->d_meta; CP.totals = ctx->d_totals;
+        CP.out = tmpbuf; CP.out_cap = pl.out_cap; CP.state = state; CP.meta = ctx->d_meta; CP.totals = ctx->d_totals;
         CP.err = ctx->d_ctr + CTR_ERR;
         const unsigned cgrid = std::min<unsigned>(n_windows, (unsigned)(ctx->sm_count * occ));
         if ((rc = begin_timed(ctx, PH_SORT))) return rc;
-        k_chunk<2><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP);
+        W_SWITCH(W, (k_sort_emit<WW><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP)));
+        // windows took their space in completion order: scan the byte counts and copy every window to its place in bucket order
+        k_out_scan<<<1, 1024, 0, ctx->stream>>>(state, n_windows, ctx->d_totals + 15);
+        k_out_gather<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(state, n_windows, tmpbuf, outbuf);
         CK(cudaGetLastError());
         if ((rc = end_timed(ctx))) return rc;
-        st->n_launches++;
+        st->n_launches += 3;
         // ---- batch epilogue: error flags, output
         unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
         unsigned long long *h_state = ctx->h_pin + 2 * NUM_BUCKETS + 8;
         CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h_state, state + (n_windows - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_state, ctx->d_totals + 15, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         st->n_giants += h_ctr[CTR_NGIANTS];
         const unsigned dev_err = h_ctr[CTR_ERR];
         if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage 2, buckets [%d,%d))", dev_err, b0, b1);
-        const unsigned long long bytes = *h_state & ((1ull << 62) - 1);
+        const unsigned long long bytes = *h_state;
         st->out_bytes += bytes;
         if (sink) {
             if (bytes > ctx->h_out_bytes) {

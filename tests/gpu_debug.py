@@ -32,8 +32,28 @@ def run(ds, k, m, **kw):
             print("  got", a[max(0, p - 8):p + 16].tolist(), "exp", b[max(0, p - 8):p + 16].tolist())
     print("  totals", totals.tolist(), et.tolist(), flush=True)
 
-if __name__ == "__main__":
-    for cap in (64, 96, 128, 512, 0):
-        run("adversarial", 21, 1, sort_items_cap=cap)
-    run("adversarial", 17, 2, sort_items_cap=64)
-    run("adversarial", 48, 2, sort_items_cap=64)
+if __name__ == "__main__" and len(sys.argv) == 1:
+    run("tiny", 21, 1)
+    run("tiny", 25, 2)
+    run("smoke", 31, 2)
+    run("smoke", 61, 2)
+
+def dump(ds, k, m, nrec=24):
+    from megagta_b200 import sdbg_io
+    prefix = datasets.materialise(ds, "/tmp/mgta_data")
+    rd = O.load_read_lib(prefix)
+    with cabi.Context(k, m) as ctx:
+        ctx.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+        if m > 1:
+            ctx.stage1()
+        stream, meta, totals = ctx.stage2()
+    es, em, et = O.stage2(rd, k, m, O.stage1(rd, k, m)[0] if m > 1 else None)
+    wpt = (2 * k + 31) // 32
+    g = sdbg_io.decode_stream(stream, wpt)
+    e = sdbg_io.decode_stream(es, wpt)
+    print(len(g), len(e))
+    for i in range(nrec):
+        print(i, g[i] if i < len(g) else None, e[i] if i < len(e) else None)
+
+if len(sys.argv) > 1 and sys.argv[1] == "dump":
+    dump("tiny", 21, 1)

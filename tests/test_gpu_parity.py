@@ -87,7 +87,7 @@ def test_gpu_small_hbm_budget_forces_batches(read_lib, ds, k, m, budget):
     _, rd = read_lib(ds)
     got = run_gpu(rd, k, m, hbm_budget_bytes=budget)
     check_vs_oracle(rd, k, m, got)
-    assert got["stats2"]["n_batches"] > 1
+    assert got["stats2"]["n_batches"] > 1 or got["stats1"]["n_batches"] > 1
 
 
 GOLDEN_CASES = ["smoke_k31_m2", "smoke_k21_m2", "smoke_k22_m2", "smoke_k32_m2", "smoke_k41_m2", "smoke_k61_m2",
