@@ -152,7 +152,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from megagta_b200 import cabi, synth
+    from megagta_b200 import cabi, shards, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,23 +197,8 @@ def main():
 
     def exchange_edges():
         """world > 1: all-gather of the solid-edge rows + all-reduce of the stage-2 prefix histogram."""
-        if world == 1:
-            return
-        ptr, n, w = ctx.edges_local()
-        counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        counts[rank] = n
-        dist.all_reduce(counts)
-        counts = [int(x) for x in counts.tolist()]
-        offs = [0]
-        for c in counts:
-            offs.append(offs[-1] + c)
-        buf_ptr = ctx.edges_reserve(offs[-1], offs[rank])
-        buf = torch.as_tensor(DevBuf(buf_ptr, max(offs[-1], 1) * w * 4), device=dev)
-        for j in range(world):
-            if counts[j]:
-                dist.broadcast(buf[offs[j] * w:offs[j + 1] * w], j)
-        hp, hb = ctx.edge_hist_device_buffer()
-        dist.all_reduce(torch.as_tensor(DevBuf(hp, hb), device=dev), op=dist.ReduceOp.SUM)
+        if world > 1:
+            shards.exchange_ctx(ctx, rank, world, dist, dev)
 
     def step(e2e):
         """-> (edges of this shard, h2d bytes, d2h bytes)"""

@@ -1,0 +1,290 @@
+// buildgraph_b200.cpp -- host-side drop-in for `megagta buildgraph` (reference src/build_graph.cpp:33-135).
+//
+// Same command line (option table of build_graph.cpp:38-48 with the defaults of cx1_read2sdbg.h:48-59), same input
+// (<X>.lib_info + <X>.bin written by `megagta buildlib`, read_lib_functions-inl.h:216-261, sequence_manager.cpp:186-213)
+// and same output files (<P>.sdbg.<i>, <P>.sdbg_info: sdbg_multi_io.h:83-112,154-198; <P>.counting: s1.cpp:925-930), so
+// the unchanged `megagta denovo / findstart / search` stages load the result as-is.  Everything between "reads in host
+// memory" and "record bytes in host memory" runs on the GPU through the C ABI of include/mgta_cuda.h; this file only
+// parses options, loads and reverses the packed reads, and writes files.  There is no CPU fallback.
+//
+//   megagta_b200 buildgraph -k 31 -m 2 --host_mem 8e9 --read_lib_file X --output_prefix P [--num_cpu_threads T ...]
+#include <errno.h>
+#include <getopt.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+#include <omp.h>
+#include <chrono>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/mgta_cuda.h"
+
+namespace {
+
+struct Options {                       // read2sdbg_opt_t, cx1_read2sdbg.h:36-59
+    int kmer_k = 21;
+    int min_count = 2;
+    double host_mem = 0;
+    double gpu_mem = 0;
+    int num_cpu_threads = 0;
+    int num_output_threads = 0;
+    std::string read_lib_file;
+    std::string assist_seq_file;
+    std::string output_prefix = "out";
+    int mem_flag = 1;
+    bool need_mercy = false;
+};
+
+[[noreturn]] void die(const std::string &msg) {
+    fprintf(stderr, "[ERROR] %s\n", msg.c_str());
+    exit(1);
+}
+
+void usage_and_exit(const char *why) {           // build_graph.cpp:77-84
+    fprintf(stderr, "%s\n", why);
+    fputs("Usage: sdbg_builder read2sdbg --read_lib_file fastx_file -o out\nOptions:\n"
+                    "  -k, --kmer_k arg                kmer size\n"
+                    "  -m, --min_kmer_frequency arg    min frequency to output an edge\n"
+                    "      --host_mem arg              Max memory to be used. 90% of the free memory is recommended.\n"
+                    "      --gpu_mem arg               gpu memory to be used. 0 for auto detect.\n"
+                    "      --num_cpu_threads arg       number of CPU threads. At least 2.\n"
+                    "      --num_output_threads arg    number of threads for output. Must be less than num_cpu_threads\n"
+                    "      --read_lib_file arg         input read library prefix (from `buildlib`)\n"
+                    "      --assist_seq arg            input assisting fast[aq] file (FILE_NAME.info should exist), can be gzip'ed.\n"
+                    "      --output_prefix arg         output prefix\n"
+                    "      --mem_flag arg              memory options (accepted for compatibility; HBM is budgeted by --gpu_mem)\n"
+                    "      --need_mercy                to add mercy edges.\n", stderr);
+    exit(1);
+}
+
+Options parse(int argc, char **argv) {
+    Options o;
+    static const struct option longopts[] = {
+        {"kmer_k", required_argument, nullptr, 'k'},          {"min_kmer_frequency", required_argument, nullptr, 'm'},
+        {"host_mem", required_argument, nullptr, 1},          {"gpu_mem", required_argument, nullptr, 2},
+        {"num_cpu_threads", required_argument, nullptr, 3},   {"num_output_threads", required_argument, nullptr, 4},
+        {"read_lib_file", required_argument, nullptr, 5},     {"assist_seq", required_argument, nullptr, 6},
+        {"output_prefix", required_argument, nullptr, 7},     {"mem_flag", required_argument, nullptr, 8},
+        {"need_mercy", no_argument, nullptr, 9},              {nullptr, 0, nullptr, 0}};
+    opterr = 0;
+    int ch;
+    while ((ch = getopt_long(argc, argv, "k:m:", longopts, nullptr)) != -1) {
+        switch (ch) {
+            case 'k': o.kmer_k = atoi(optarg); break;
+            case 'm': o.min_count = atoi(optarg); break;
+            case 1: o.host_mem = atof(optarg); break;
+            case 2: o.gpu_mem = atof(optarg); break;
+            case 3: o.num_cpu_threads = atoi(optarg); break;
+            case 4: o.num_output_threads = atoi(optarg); break;
+            case 5: o.read_lib_file = optarg; break;
+            case 6: o.assist_seq_file = optarg; break;
+            case 7: o.output_prefix = optarg; break;
+            case 8: o.mem_flag = atoi(optarg); break;
+            case 9: o.need_mercy = true; break;
+            default: usage_and_exit("uknown option");           // options_description.cpp:69-70 (sic)
+        }
+    }
+    // the checks of build_graph.cpp:53-75, same messages
+    if (o.read_lib_file.empty()) usage_and_exit("No input file!");
+    if (o.num_cpu_threads == 0) o.num_cpu_threads = omp_get_max_threads();
+    if (o.num_output_threads == 0) o.num_output_threads = std::max(1, o.num_cpu_threads / 3);
+    if (o.host_mem == 0) usage_and_exit("Please specify the host memory!");
+    if (o.num_cpu_threads == 1) usage_and_exit("Number of CPU threads should be at least 2!");
+    if (o.num_output_threads >= o.num_cpu_threads) usage_and_exit("Number of output threads must be less than number of CPU threads!");
+    return o;
+}
+
+// ---- read library -> reversed, bit-contiguous packed reads (what ReadBinaryLibs(..., is_reverse = true) builds:
+// read_lib_functions-inl.h:233-261, SequencePackage::AppendRevSeq sequence_package.h:247-252,341-367)
+struct Reads {
+    uint32_t *seq = nullptr;           // malloc'ed, n_words
+    uint64_t n_words = 0;
+    std::vector<uint64_t> start;       // n_reads + 1
+    uint64_t n_reads = 0;
+    int max_len = 0;
+};
+
+Reads load_read_lib(const std::string &prefix, int threads) {
+    Reads R;
+    long long total_bases = 0, num_reads = 0;
+    {
+        FILE *f = fopen((prefix + ".lib_info").c_str(), "r");
+        if (!f) die("cannot open " + prefix + ".lib_info: " + strerror(errno));
+        if (fscanf(f, "%lld %lld", &total_bases, &num_reads) != 2) die("bad first line in " + prefix + ".lib_info");
+        fclose(f);
+    }
+    gzFile gz = gzopen((prefix + ".bin").c_str(), "rb");        // the reference reads .bin through gzread, too
+    if (!gz) die("cannot open " + prefix + ".bin");
+    gzbuffer(gz, 1 << 22);
+    // pass 1: raw records into memory (u32 len, ceil(len/16) words, forward orientation), offsets per read
+    std::vector<uint32_t> raw;
+    raw.reserve((size_t)(total_bases / 16 + 2 * num_reads + 16));
+    std::vector<uint64_t> rec_off;
+    rec_off.reserve((size_t)num_reads);
+    R.start.reserve((size_t)num_reads + 1);
+    R.start.push_back(0);
+    uint64_t bases = 0;
+    for (;;) {
+        uint32_t len;
+        int got = gzread(gz, &len, 4);
+        if (got == 0) break;
+        if (got != 4) die("truncated record header in " + prefix + ".bin");
+        const uint32_t nw = (len + 15) / 16;
+        const size_t at = raw.size();
+        raw.resize(at + nw);
+        if (nw && gzread(gz, raw.data() + at, nw * 4) != (int)(nw * 4)) die("truncated record in " + prefix + ".bin");
+        rec_off.push_back(at);
+        bases += len;
+        R.start.push_back(bases);
+        R.max_len = std::max<int>(R.max_len, (int)len);
+    }
+    gzclose(gz);
+    R.n_reads = rec_off.size();
+    if ((long long)R.n_reads != num_reads || (long long)bases != total_bases)
+        die("read library " + prefix + ": .bin holds " + std::to_string(R.n_reads) + " reads / " + std::to_string(bases) +
+            " bases, .lib_info says " + std::to_string(num_reads) + " / " + std::to_string(total_bases));
+    R.n_words = bases / 16 + 1;
+    R.seq = (uint32_t *)calloc(R.n_words + 4, 4);
+    if (!R.seq) die("out of host memory for the packed reads");
+    // pass 2: reverse each read into its bit range; reads are independent except for shared boundary words (atomic OR)
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
+    for (long long r = 0; r < (long long)R.n_reads; ++r) {
+        const uint32_t *w = raw.data() + rec_off[(size_t)r];
+        const uint64_t s = R.start[(size_t)r];
+        const int L = (int)(R.start[(size_t)r + 1] - s);
+        uint64_t g = s;
+        uint32_t acc = 0;
+        int filled = (int)(g & 15);                            // bases already belonging to other reads in the first word
+        uint64_t word = g >> 4;
+        for (int i = L - 1; i >= 0; --i) {                     // reversed, not complemented
+            const uint32_t c = (w[i >> 4] >> ((15 - (i & 15)) * 2)) & 3u;
+            acc |= c << ((15 - filled) * 2);
+            if (++filled == 16) {
+                __atomic_fetch_or(&R.seq[word], acc, __ATOMIC_RELAXED);
+                acc = 0; filled = 0; ++word;
+            }
+        }
+        if (filled) __atomic_fetch_or(&R.seq[word], acc, __ATOMIC_RELAXED);
+    }
+    return R;
+}
+
+// ---- SdbgWriter equivalent: one record file per shard (here one), sdbg_info in the reference's exact text format
+struct Writer {
+    std::string prefix;
+    FILE *f = nullptr;
+    long long offset = 0;
+    std::vector<long long> file_id, start, n_items, n_tips, n_large;
+    Writer() : file_id(MGTA_NUM_BUCKETS, -1), start(MGTA_NUM_BUCKETS, 0), n_items(MGTA_NUM_BUCKETS, 0), n_tips(MGTA_NUM_BUCKETS, 0),
+               n_large(MGTA_NUM_BUCKETS, 0) {}
+};
+
+int sink(void *user, int32_t b0, int32_t b1, const void *bytes, uint64_t n_bytes, const int64_t *meta) {
+    Writer *w = (Writer *)user;
+    if (n_bytes && fwrite(bytes, 1, n_bytes, w->f) != n_bytes) return -1;
+    long long off = w->offset;
+    for (int b = b0; b < b1; ++b) {
+        const int64_t *m = meta + (size_t)(b - b0) * 3;
+        w->n_items[b] = m[0]; w->n_tips[b] = m[1]; w->n_large[b] = m[2];
+        if (m[0]) { w->file_id[b] = 0; w->start[b] = off; }
+        off += m[0] * 2 + m[2] * 2;                             // u16 record (+ u16 multiplicity), filled in below with tip words
+    }
+    w->offset += (long long)n_bytes;
+    return 0;
+}
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int build_graph(int argc, char **argv) {
+    const double t0 = now();
+    Options opt = parse(argc, argv);
+    if (!opt.assist_seq_file.empty()) die("--assist_seq is not supported by the B200 driver yet (SURVEY 8f row 2)");
+    if (opt.need_mercy) die("--need_mercy is not supported by the B200 driver yet (SURVEY 8f row 1)");
+
+    Reads R = load_read_lib(opt.read_lib_file, opt.num_cpu_threads);
+    fprintf(stderr, "[B200] %llu reads, %llu bases, max length %d, loaded in %.2f s\n", (unsigned long long)R.n_reads,
+            (unsigned long long)R.start.back(), R.max_len, now() - t0);
+    if (R.n_reads == 0) die("empty read library");
+
+    mgta_opts mo;
+    memset(&mo, 0, sizeof(mo));
+    mo.kmer_k = opt.kmer_k; mo.min_count = opt.min_count; mo.need_mercy = 0;
+    mo.device = 0; mo.rank = 0; mo.world = 1;
+    mo.hbm_budget_bytes = (int64_t)opt.gpu_mem;                 // 0 = 90 % of the free HBM, as the reference's "auto detect"
+    mgta_ctx *ctx = nullptr;
+    if (mgta_ctx_create(&mo, &ctx) != 0) die(std::string("mgta_ctx_create: ") + mgta_last_error(nullptr));
+    auto ck = [&](int rc, const char *what) { if (rc != 0) die(std::string(what) + ": " + mgta_last_error(ctx)); };
+
+    const double t1 = now();
+    ck(mgta_set_reads(ctx, R.seq, R.n_words, R.start.data(), R.n_reads, R.n_reads, R.max_len), "mgta_set_reads");
+    if (opt.min_count > 1) {
+        std::vector<int64_t> ec(MGTA_NUM_BUCKETS, 0);
+        ck(mgta_stage1(ctx, ec.data()), "mgta_stage1");
+        FILE *cf = fopen((opt.output_prefix + ".counting").c_str(), "w");     // s1.cpp:925-930
+        if (!cf) die("cannot write " + opt.output_prefix + ".counting");
+        long long acc = 0;
+        for (int i = 1; i <= 65535; ++i) { acc += ec[i]; fprintf(cf, "%lld %lld\n", (long long)i, acc); }
+        fclose(cf);
+        long long solid = 0;
+        for (int i = opt.min_count; i <= 65535; ++i) solid += ec[i];
+        fprintf(stderr, "[B200] Total number of solid edges: %lld\n", solid);
+    }
+    Writer W;
+    W.prefix = opt.output_prefix;
+    W.f = fopen((opt.output_prefix + ".sdbg.0").c_str(), "wb");
+    if (!W.f) die("cannot write " + opt.output_prefix + ".sdbg.0");
+    int64_t totals[10];
+    ck(mgta_stage2(ctx, sink, &W, totals), "mgta_stage2");
+    fclose(W.f);
+    const double t2 = now();
+
+    // exact byte offsets of the buckets inside the file (records + tip labels)
+    const int wpt = (2 * opt.kmer_k + 31) / 32;
+    {
+        long long off = 0;
+        for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) {
+            if (W.n_items[b]) W.start[b] = off;
+            off += W.n_items[b] * 2 + W.n_large[b] * 2 + W.n_tips[b] * 4LL * wpt;
+        }
+        if (off != W.offset) die("internal: bucket table does not add up to the record stream");
+    }
+    FILE *info = fopen((opt.output_prefix + ".sdbg_info").c_str(), "w");       // sdbg_multi_io.h:160-187
+    if (!info) die("cannot write " + opt.output_prefix + ".sdbg_info");
+    long long te = 0, tt = 0, tl = 0;
+    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) { te += W.n_items[b]; tt += W.n_tips[b]; tl += W.n_large[b]; }
+    fprintf(info, "k %d\n", opt.kmer_k);
+    fprintf(info, "words_per_tip_label %d\n", wpt);
+    fprintf(info, "num_buckets %d\n", MGTA_NUM_BUCKETS);
+    fprintf(info, "num_threads %d\n", 1);
+    fprintf(info, "total_size %lld\n", te);
+    fprintf(info, "num_tips %lld\n", tt);
+    fprintf(info, "large_multi %lld\n", tl);
+    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b)
+        fprintf(info, "%d %d %lld %lld %lld %lld\n", b, (int)W.file_id[b], W.start[b], W.n_items[b], W.n_tips[b], W.n_large[b]);
+    fclose(info);
+
+    mgta_stage_stats s1, s2;
+    mgta_get_stats(ctx, 1, &s1);
+    mgta_get_stats(ctx, 2, &s2);
+    fprintf(stderr, "[B200] stage 1: %.1f ms device (%llu items), stage 2: %.1f ms device (%llu items, %lld edges); "
+                    "reads-in-host-memory -> files: %.2f s\n", s1.ms_total, (unsigned long long)s1.n_items, s2.ms_total,
+            (unsigned long long)s2.n_items, te, t2 - t1);
+    fprintf(stderr, "Real: %.4f\n", now() - t0);                 // utils.h:124 prints the same line
+    mgta_ctx_destroy(ctx);
+    free(R.seq);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2 || strcmp(argv[1], "buildgraph") != 0) {
+        fprintf(stderr, "usage: %s buildgraph [options]   (drop-in for `megagta buildgraph`, reference src/megagta.cpp:28-60)\n", argv[0]);
+        return 1;
+    }
+    return build_graph(argc - 1, argv + 1);
+}
