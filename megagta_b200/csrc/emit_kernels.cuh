@@ -31,6 +31,104 @@ __device__ __forceinline__ int key_cmp(const uint32_t *keys, unsigned capi, unsi
     return 0;
 }
 
+// Bucket + rank sort of one window: the items are distinct-edge items, so below the `kb` key bits the window shares they
+// are close to uniformly spread.  One counting pass over the next D key bits (shared-memory atomics give the arrival
+// rank inside a bin), an exclusive scan of the <= 4096 bin counters, and a comparison rank inside each bin (bins hold
+// the few items of one (k-1)-mer group plus chance collisions) replace the 1 + ceil((2(k-1) - kb) / 8) LSD passes.
+// Returns false (uniformly, nothing written to S.pa) when a bin holds more than P.big_bin items: low-complexity windows
+// take the LSD path below.
+
+template <int W>
+__device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *hist, unsigned capi, unsigned n, int kb, int D,
+                                                 unsigned *s_big, unsigned big_bin) {
+    const unsigned NB = 1u << D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (unsigned i = tid; i < NB; i += CHUNK_THREADS) hist[i] = 0;
+    if (tid == 0) *s_big = 0;
+    __syncthreads();
+    unsigned short dg[8], rk[8];
+    bool big = false;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const unsigned i = tid + r * CHUNK_THREADS;
+        if (i < n) {
+            const unsigned d = (S.keys[i] << kb) >> (32 - D);
+            const unsigned a = atomicAdd(&hist[d], 1u);
+            dg[r] = (unsigned short)d; rk[r] = (unsigned short)a;
+            big = big || a >= big_bin;
+        }
+    }
+    if (big) *s_big = 1;
+    __syncthreads();
+    if (*s_big) return false;
+    // exclusive scan of the bin counters: `per` consecutive counters per thread
+    {
+        const unsigned per = NB >= CHUNK_THREADS ? NB / CHUNK_THREADS : 1u;       // <= 8
+        unsigned c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned b = tid * per + j;
+            c[j] = ((unsigned)j < per && b < NB) ? hist[b] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const unsigned t = c[j]; c[j] = sum; sum += t; }
+        unsigned x = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, off);
+            if (lane >= (unsigned)off) x += y;
+        }
+        if (lane == 31) S.scan[warp] = x;
+        __syncthreads();
+        unsigned ws = lane < CHUNK_WARPS ? S.scan[lane] : 0u;                      // inclusive scan of the warp totals
+#pragma unroll
+        for (int off = 1; off < CHUNK_WARPS; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xFFFFFFFFu, ws, off);
+            if (lane >= (unsigned)off) ws += y;
+        }
+        const unsigned add = warp ? __shfl_sync(0xFFFFFFFFu, ws, warp - 1) : 0u;
+        const unsigned excl = x - sum + add;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned b = tid * per + j;
+            if ((unsigned)j < per && b < NB) hist[b] = excl + c[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const unsigned i = tid + r * CHUNK_THREADS;
+        if (i < n) S.pb[hist[dg[r]] + rk[r]] = (uint16_t)i;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const unsigned i = tid + r * CHUNK_THREADS;
+        if (i < n) {
+            const unsigned d = dg[r];
+            const unsigned s = hist[d], e = d + 1 < NB ? hist[d + 1] : n;
+            unsigned pos = s;
+            if (e - s > 1) {
+                uint32_t mine[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) mine[w] = S.keys[w * capi + i];
+                for (unsigned j = s; j < e; ++j) {
+                    const unsigned o = S.pb[j];
+                    bool less = o < i;                                             // equal keys: by item index
+#pragma unroll
+                    for (int w = W - 1; w >= 0; --w) {
+                        const uint32_t x = S.keys[w * capi + o];
+                        less = x < mine[w] || (x == mine[w] && less);
+                    }
+                    pos += (o != i && less) ? 1u : 0u;
+                }
+            }
+            S.pa[pos] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 template <int W>
 __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -53,7 +151,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
     }
     uint32_t *code = fld;                                      // per sorted position: group / run bits, a, b, multiplicity
     __shared__ unsigned long long s_lo, s_hi, s_base;
-    __shared__ unsigned s_j2[2], s_tot10[10];
+    __shared__ unsigned s_j2[2], s_tot10[10], s_big;
     if (tid < 10) s_tot10[tid] = 0;
 
     for (unsigned iter = 0;; ++iter) {
@@ -83,7 +181,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
         // ---- LSD radix sort of the permutation by the whole key: pass 0 = the 6-bit in-group order (a slot, a != $, b),
         //      then the S bits [kb, 2(k-1)) from the least significant byte up.  One __match_any_sync per item and pass;
         //      digit, warp-local rank and item stay in registers between the counting and the scatter half.
-        if (n > 1) {
+        bool sorted = n <= 1;
+        if (!sorted && P.bin_bits > 0) sorted = bucket_rank_sort<W>(S, fld, capi, n, kb, P.bin_bits, &s_big, P.big_bin);
+        if (!sorted) {
+            if (tid == 0 && P.n_lsd) atomicAdd(P.n_lsd, 1u);
             const unsigned slice = (((n + CHUNK_WARPS - 1) / CHUNK_WARPS) + 31) & ~31u;
             const unsigned beg = min(n, warp * slice), end = min(n, beg + slice);
             const unsigned rounds = (end - beg + 31) >> 5;    // <= capi / 512 <= 8

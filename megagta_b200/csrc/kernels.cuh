@@ -273,6 +273,9 @@ struct ChunkParams {
     const uint32_t *win_giant;
     const Giant *giants;
     int depth_min;
+    unsigned *n_lsd;                         // windows that took the LSD passes (statistics)
+    unsigned big_bin;                        // largest bin the comparison rank accepts
+    int bin_bits;                            // bucket + rank sort: key bits of the counting pass (0 = LSD passes only)
     int n_pass;
     short pass_lsb[MAX_PASSES];
     unsigned char pass_nb[MAX_PASSES];

@@ -978,6 +978,12 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         CP.src = bufB; CP.cap = pl.cap; CP.n_items = n_items; CP.W = pl.W; CP.IW = pl.IW; CP.k = pl.k;
         CP.CAPI = pl.CAPI; CP.C = pl.C; CP.n_windows = n_windows; CP.ticket = ctx->d_ctr + CTR_TICKET;
         CP.flags = flags; CP.win_giant = win; CP.giants = giants; CP.depth_min = std::min(PB, 2 * (k - 1));
+        CP.n_lsd = ctx->d_ctr + CTR_NOVF;
+        CP.big_bin = 64;
+        if (const char *e = getenv("MGTA_SORT_BIG_BIN")) CP.big_bin = (unsigned)std::max(1, atoi(e));
+        CP.bin_bits = 0;
+        while (CP.bin_bits < 12 && (2u << CP.bin_bits) <= pl.CAPI) ++CP.bin_bits;             // bins <= CAPI counters (the code array)
+        if (const char *e = getenv("MGTA_SORT_BIN_BITS")) CP.bin_bits = std::max(0, std::min(CP.bin_bits, atoi(e)));   // A/B switch: 0 = LSD only
         CP.n_pass = pl.n_pass;
         memcpy(CP.pass_lsb, pl.pass_lsb, sizeof(CP.pass_lsb));
         memcpy(CP.pass_nb, pl.pass_nb, sizeof(CP.pass_nb));
@@ -1002,7 +1008,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_state, ctx->d_totals + 15, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        st->n_giants += h_ctr[CTR_NGIANTS];
+        st->n_giants += h_ctr[CTR_NGIANTS] + h_ctr[CTR_NOVF];      // windows sorted by the LSD passes (low-complexity or forced)
         const unsigned dev_err = h_ctr[CTR_ERR];
         if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage 2, buckets [%d,%d))", dev_err, b0, b1);
         const unsigned long long bytes = *h_state;
