@@ -172,28 +172,56 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
     __syncthreads();
     const uint64_t r_lo = s_r[0], r_hi = s_r[1];
     const int k = P.k;
-#pragma unroll 1
-    for (int it = 0; it < TP / PART_THREADS; ++it) {
-        const int slot = it * PART_THREADS + tid;
-        const uint64_t g = g0 + (uint64_t)slot;
+    // Each thread ROLLS over RUN consecutive edge offsets: the (k+1)-mer E and its reverse complement R are cut out of
+    // the staged words once and then advanced one base at a time (the device counterpart of the reference's
+    // ShiftAppend / ShiftPreappend, megahit_kmer.h:151-174), and the read the position lies in is tracked incrementally.
+    constexpr int RUN = TP / PART_THREADS;
+    const uint64_t gt = g0 + (uint64_t)tid * RUN;
+    const uint32_t q0 = (uint32_t)(gt - 16 * w_lo);
+    uint32_t E[WE], R[WE];
+    uint64_t r = 0, s_next = 0;
+    if (gt < gend) {
+        r = find_read(P.start, r_lo, r_hi, gt);
+        s_next = __ldg(P.start + r + 1);
+        load_chars<WE>(sw, q0, k + 1, E);
+        revcomp<WE>(E, k + 1, R);
+    }
+    const int cw = k >> 4, csh = (15 - (k & 15)) * 2;             // word / shift of char index k (the last char of the edge)
+    const uint32_t tail_mask = head_mask(k + 1 - 16 * (WE - 1));
+    const unsigned sub_mask = (1u << P.lb2) - 1u;
+#pragma unroll
+    for (int j = 0; j < RUN; ++j) {
+        const int slot = j * PART_THREADS + tid;                  // any slot numbering works: this one is bank-conflict free
+        const uint64_t g = gt + (uint64_t)j;
         unsigned bin = 0xFFFFu;
         if (g < gend) {
-            const uint64_t r = find_read(P.start, r_lo, r_hi, g);
-            const uint64_t s = __ldg(P.start + r);
-            const int64_t L = (int64_t)(__ldg(P.start + r + 1) - s);
-            const int64_t p = (int64_t)(g - s);
-            bool ok = L >= k + 1 && p < L - k;
+            if (j > 0) {
+                const uint32_t c = (uint32_t)char_at(sw, q0 + (uint32_t)(j + k));
+#pragma unroll
+                for (int w = 0; w < WE; ++w) {
+                    E[w] = (w + 1 < WE) ? __funnelshift_l(E[w + 1 < WE ? w + 1 : w], E[w], 2) : (E[w] << 2);
+                    if (w == cw) E[w] |= c << csh;
+                }
+#pragma unroll
+                for (int w = WE - 1; w >= 0; --w)
+                    R[w] = (w > 0) ? __funnelshift_r(R[w], R[w > 0 ? w - 1 : 0], 2) : ((R[0] >> 2) | ((3u - c) << 30));
+                R[WE - 1] &= tail_mask;
+            }
+            while (g >= s_next) { ++r; s_next = __ldg(P.start + r + 1); }
+            bool ok = g + (uint64_t)k + 1 <= s_next;              // the whole (k+1)-mer lies inside read r
             const bool assist = r >= P.n_short;
             if (ok && P.filter) ok = P.all_solid || assist || bit_at(P.solid, g);
             if (ok) {
+                const bool fw = cmp_words<WE>(E, R) <= 0;
                 uint32_t key[WE];
-                canonical_edge<WE>(sw, (uint32_t)(g - 16 * w_lo), k, key);
+#pragma unroll
+                for (int w = 0; w < WE; ++w) key[w] = fw ? E[w] : R[w];
                 uint32_t ha, hb;
                 edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
                 const unsigned b1 = ha >> P.sh1;
                 if (b1 >= P.b_lo && b1 < P.b_hi) {
                     bin = b1 - P.b_lo;
-                    atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & ((1u << P.lb2) - 1u))), 1u);
+                    atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & sub_mask)), 1u);
 #pragma unroll
                     for (int w = 0; w < WE; ++w) S.stage[w * TP + slot] = key[w];
                     if (PW >= 1) S.stage[WE * TP + slot] = assist ? 0xFFFFFFFFu : (uint32_t)g;
