@@ -474,7 +474,13 @@ int launch_edge_part_t(int WE, const EdgePartParams &P, unsigned grid, cudaStrea
     return e == cudaSuccess ? 0 : -1;
 }
 
-int edge_tile_positions(int IW) { return IW <= 3 ? 4096 : (IW <= 6 ? 2048 : 1024); }
+// positions per k_edge_part CTA: as many as shared memory allows with >= 2 CTAs per SM (1024 level-1 bins per CTA: a small
+// tile leaves runs of 1-2 items per bin, i.e. one cursor atomic and one partial sector per item)
+int edge_tile_positions(int IW) {
+    int tp = IW <= 4 ? 4096 : (IW <= 9 ? 2048 : 1024);
+    if (const char *e = getenv("MGTA_EDGE_TP")) { const int v = atoi(e); if (v == 1024 || v == 2048 || v == 4096) tp = v; }   // A/B switch
+    return tp;
+}
 
 int launch_edge_part(int WE, int PW, const EdgePartParams &P, uint64_t total_bases, cudaStream_t st) {
     const int TP = edge_tile_positions(WE + PW);
@@ -579,13 +585,16 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
     // per-tile table: sized so that two CTAs share an SM; overflow tiles get the largest table that fits one SM
     const size_t slot_bytes = 4 * (size_t)(2 + (has_assist ? 1 : 0) + WE) + 2;
     unsigned tab_cap = 4096, big_cap = 16384;
-    while (tab_cap > 1024 && tab_cap * slot_bytes > 96 * 1024) tab_cap >>= 1;
+    while (tab_cap > 1024 && tab_cap * slot_bytes > 106 * 1024) tab_cap >>= 1;       // 2 x (106 KB + static) fit one SM
     while (big_cap > tab_cap && big_cap * slot_bytes > 200 * 1024) big_cap >>= 1;
     unsigned tab_limit = tab_cap - 640;                            // COUNT_THREADS inserts may be in flight past the check
     if (ctx->opt.sort_items_cap > 0) tab_limit = std::min<unsigned>(tab_limit, std::max(8, ctx->opt.sort_items_cap));   // test hook: force the overflow pass
     // tiles of about tab_cap / 2 items: level-2 fan-out <= 1024, level-1 bins as many as it takes (a batch handles <= 1024)
     int bits = 2;
-    while (bits < 28 && (n_pos >> bits) > (uint64_t)tab_cap * 6 / 10) ++bits;
+    // mean tile = up to 3/4 of the table (a Poisson tail of 6 sigma still fits below tab_limit; denser tiles only pay the
+    // overflow pass).  Keeping the mean high matters: one more bit doubles the level-1 bins, and past MAX_BINS the reads
+    // are scanned once per batch of bins.
+    while (bits < 28 && (n_pos >> bits) > (uint64_t)tab_cap * 3 / 4) ++bits;
     const unsigned lb2 = (unsigned)std::min(10, bits / 2), lb1 = (unsigned)bits - lb2;
     const unsigned B1 = 1u << lb1;
     const unsigned T = split_chunk_items(IW);

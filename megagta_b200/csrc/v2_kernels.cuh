@@ -24,6 +24,7 @@ namespace mgta {
 
 constexpr int PART_THREADS = 512;
 constexpr int MAX_BINS = 1024;
+constexpr int MAX_OWNERS = 16;        // shards of one scan-sharded exchange (GPUs of one NVSwitch domain)
 constexpr int COUNT_THREADS = 512;
 constexpr uint32_t TAG_EMPTY = 0u, TAG_LOCK = 0xFFFFFFFFu, TAG_DEAD = 0xFFFFFFFEu;
 enum { ERR_SLAB_OVERFLOW = 16, ERR_EDGE_LIST_FULL = 32, ERR_OVF_LIST_FULL = 64, ERR_TABLE_FULL = 128 };
@@ -73,9 +74,12 @@ __device__ __forceinline__ void bin_smem_carve(BinSmem &S, unsigned char *p, int
 
 // Precondition: S.cnt / S.bin / S.rank / S.stage filled for slots [0, n_slots), block synchronised.
 // cursor[b]: next free absolute item index of bin b in dst; slab_cap != 0: bin b may only use indices
-// below (b + 1) * slab_cap (optimistic fixed-capacity slabs; overflow is flagged, never written).
+// [b * slab_stride, b * slab_stride + slab_cap) (optimistic fixed-capacity slabs; overflow is flagged, never written;
+// slab_stride defaults to slab_cap).
 __device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int P, int NB, unsigned long long *cursor,
-                                            uint32_t *dst, uint64_t cap, unsigned long long slab_cap, unsigned *err) {
+                                            uint32_t *dst, uint64_t cap, unsigned long long slab_cap, unsigned *err,
+                                            unsigned long long slab_stride = 0) {
+    if (slab_stride == 0) slab_stride = slab_cap;                 // slab b holds indices [b * stride, b * stride + slab_cap)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (NB + PART_THREADS - 1) / PART_THREADS;       // <= 4
     unsigned local[4], c_[4], sum = 0;
@@ -120,7 +124,7 @@ __device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int
     for (unsigned j = tid; j < total; j += PART_THREADS) {
         const unsigned i = S.perm[j], b = S.bin[i];
         const unsigned long long g = S.gbase[b] + (j - S.lbase[b]);
-        if (slab_cap && g >= (unsigned long long)(b + 1) * slab_cap) { over = true; continue; }
+        if (slab_cap && g >= (unsigned long long)b * slab_stride + slab_cap) { over = true; continue; }
         for (int w = 0; w < IW; ++w) dst[(uint64_t)w * cap + g] = S.stage[w * P + i];
     }
     if (over) atomicOr(err, (unsigned)ERR_SLAB_OVERFLOW);
@@ -144,6 +148,13 @@ struct EdgePartParams {
     uint32_t *dst;
     uint64_t cap;
     unsigned *err;
+    // scan-sharded mode (n_owner > 0): only reads [r_begin, r_end) are scanned (CTA tiles start at base g_begin, a multiple
+    // of 1024), and the bin of an item is the SHARD that owns its level-1 hash bin: owner d holds bins
+    // [owner_lo[d], owner_lo[d + 1]).  Slab d starts at item index d * slab_stride; no tile histogram is taken.
+    int n_owner;
+    unsigned owner_lo[MAX_OWNERS + 1];
+    uint64_t g_begin, g_end, r_begin;
+    unsigned long long slab_stride;
 };
 
 // PW = payload words: 0 none, 1 = base position (u32), 2 = base position (lo, hi)
@@ -157,9 +168,9 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, TP);
     const int tid = threadIdx.x;
-    const int NB = (int)(P.b_hi - P.b_lo);
-    const uint64_t g0 = (uint64_t)blockIdx.x * TP;
-    const uint64_t gend = min(g0 + (uint64_t)TP, P.total_bases);
+    const int NB = P.n_owner ? P.n_owner : (int)(P.b_hi - P.b_lo);
+    const uint64_t g0 = (P.n_owner ? P.g_begin : 0ull) + (uint64_t)blockIdx.x * TP;
+    const uint64_t gend = min(g0 + (uint64_t)TP, P.n_owner ? P.g_end : P.total_bases);
     const uint64_t w_lo = (g0 >> 4) >= WALK_BACK_WORDS ? (g0 >> 4) - WALK_BACK_WORDS : 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.seq + w_lo);
@@ -211,6 +222,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
             bool ok = g + (uint64_t)k + 1 <= s_next;              // the whole (k+1)-mer lies inside read r
             const bool assist = r >= P.n_short;
             if (ok && P.filter) ok = P.all_solid || assist || bit_at(P.solid, g);
+            if (ok && P.n_owner) ok = r >= P.r_begin;             // lead-in of the first tile belongs to the previous read
             if (ok) {
                 const bool fw = cmp_words<WE>(E, R) <= 0;
                 uint32_t key[WE];
@@ -219,9 +231,21 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
                 uint32_t ha, hb;
                 edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
                 const unsigned b1 = ha >> P.sh1;
-                if (b1 >= P.b_lo && b1 < P.b_hi) {
-                    bin = b1 - P.b_lo;
-                    atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & sub_mask)), 1u);
+                bool mine;
+                if (P.n_owner) {
+                    unsigned d = 0;
+#pragma unroll
+                    for (int i = 1; i < MAX_OWNERS; ++i) d += (i < P.n_owner && b1 >= P.owner_lo[i]) ? 1u : 0u;
+                    bin = d;
+                    mine = true;
+                } else {
+                    mine = b1 >= P.b_lo && b1 < P.b_hi;
+                    if (mine) {
+                        bin = b1 - P.b_lo;
+                        atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & sub_mask)), 1u);
+                    }
+                }
+                if (mine) {
 #pragma unroll
                     for (int w = 0; w < WE; ++w) S.stage[w * TP + slot] = key[w];
                     if (PW >= 1) S.stage[WE * TP + slot] = assist ? 0xFFFFFFFFu : (uint32_t)g;
@@ -233,7 +257,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
         S.bin[slot] = (uint16_t)bin;
     }
     __syncthreads();
-    bin_scatter(S, TP, IW, TP, NB, P.cursor1, P.dst, P.cap, P.slab_cap, P.err);
+    bin_scatter(S, TP, IW, TP, NB, P.cursor1, P.dst, P.cap, P.slab_cap, P.err, P.n_owner ? P.slab_stride : 0ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,7 +356,8 @@ struct SplitParams {
     uint32_t *dst;
     uint64_t cap_src, cap_dst;
     int IW, WE;
-    int mode;                            // 0: hash of the WE key words, 1: prefix bits of key word 0
+    int mode;                            // 0: hash of the WE key words, 1: prefix bits of key word 0,
+                                         // 2: level-1 hash bin of items received from the other shards (see below)
     int sh2;                             // tile = x >> sh2 (x = ha or key word 0)
     unsigned lb2;
     const unsigned long long *in_start;  // [B1]
@@ -343,6 +368,13 @@ struct SplitParams {
     unsigned *ticket;
     unsigned T;
     unsigned *err;
+    // mode 2: the input regions are the slabs received from the shards; all of them feed ONE set of level-1 bins
+    // [b_lo, b_hi) (bin = ha >> sh1; items of other bins are skipped: a later batch takes them), written to fixed-capacity
+    // slabs through cursor2[bin] like k_edge_part does, and the tile histogram hist2 is accumulated on the way.
+    int sh1;
+    unsigned b_lo, b_hi;
+    unsigned long long slab_cap;
+    uint32_t *hist2;
 };
 
 __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
@@ -351,7 +383,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
     BinSmem S;
     const int T = (int)P.T, IW = P.IW, tid = threadIdx.x;
     bin_smem_carve(S, smem_raw, IW, T);
-    const int NB = 1 << P.lb2;
+    const int NB = P.mode == 2 ? (int)(P.b_hi - P.b_lo) : 1 << P.lb2;
     const unsigned n_jobs = P.chunk_pref[P.B1];
     if (*P.err & ERR_SLAB_OVERFLOW) return;
     while (true) {
@@ -383,18 +415,31 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
         __syncthreads();
         for (int i = tid; i < n; i += PART_THREADS) {
             uint32_t x;
-            if (P.mode == 0) {
+            if (P.mode != 1) {
                 uint32_t hb;
                 edge_hash([&](int w) { return S.stage[w * T + i]; }, P.WE, x, hb);
             } else {
                 x = S.stage[i];
+            }
+            if (P.mode == 2) {
+                const unsigned bb = x >> P.sh1;
+                if (bb >= P.b_lo && bb < P.b_hi) {
+                    const unsigned b = bb - P.b_lo;
+                    atomicAdd(P.hist2 + ((b << P.lb2) | ((x >> P.sh2) & ((1u << P.lb2) - 1u))), 1u);
+                    S.bin[i] = (uint16_t)b;
+                    S.rank[i] = (uint16_t)atomicAdd(&S.cnt[b], 1u);
+                } else {
+                    S.bin[i] = 0xFFFFu;
+                }
+                continue;
             }
             const unsigned b2 = (x >> P.sh2) & (unsigned)(NB - 1);
             S.bin[i] = (uint16_t)b2;
             S.rank[i] = (uint16_t)atomicAdd(&S.cnt[b2], 1u);
         }
         __syncthreads();
-        bin_scatter(S, n, IW, T, NB, P.cursor2 + ((size_t)b1 << P.lb2), P.dst, P.cap_dst, 0ull, P.err);
+        if (P.mode == 2) bin_scatter(S, n, IW, T, NB, P.cursor2, P.dst, P.cap_dst, P.slab_cap, P.err);
+        else bin_scatter(S, n, IW, T, NB, P.cursor2 + ((size_t)b1 << P.lb2), P.dst, P.cap_dst, 0ull, P.err);
     }
 }
 
@@ -426,11 +471,11 @@ struct CountParams {
 
 struct CountSmem {
     uint32_t *tag, *cnt, *acnt, *keys;
-    uint16_t *emit, *list;            // slots to emit; slots claimed for this tile (the only ones that need clearing)
+    uint16_t *list;                   // slots claimed for this tile (the only ones that need clearing)
 };
 
 __host__ __device__ inline size_t count_smem_bytes(int WE, unsigned cap, int has_assist) {
-    return (size_t)cap * 4 * (2 + (has_assist ? 1 : 0) + WE) + (size_t)cap * 4;
+    return (size_t)cap * 4 * (2 + (has_assist ? 1 : 0) + WE) + (size_t)cap * 2;
 }
 
 template <int WE>
@@ -467,10 +512,9 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
         S.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4 * WE;
         S.acnt = S.cnt;
         if (P.has_assist) { S.acnt = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4; }
-        S.emit = reinterpret_cast<uint16_t *>(p); p += (size_t)cap * 2;
         S.list = reinterpret_cast<uint16_t *>(p);
     }
-    __shared__ unsigned s_tile2[2], s_ndist, s_sawlock, s_nemit, s_ec[256];
+    __shared__ unsigned s_tile2[2], s_ndist, s_sawlock, s_nemit, s_ec[256], s_wsum[COUNT_THREADS / 32];
     __shared__ unsigned long long s_ebase;
     for (unsigned i = tid; i < 256; i += COUNT_THREADS) s_ec[i] = 0;
     const unsigned n_tiles = P.tile_list ? *P.n_tile_list : P.t_hi - P.t_lo;
@@ -581,7 +625,9 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
                 }
             }
         }
-        // ---- phase C: per distinct edge: edge_counting (s1.cpp:744-746) and the solid edge list
+        // ---- phase C: per distinct edge: edge_counting (s1.cpp:744-746) and the solid edge list.  Two walks over this
+        //      thread's claimed slots: count the rows it will write, block scan + one global reservation, write them.
+        unsigned my_rows = 0;
         for (unsigned li = tid; li < nd; li += COUNT_THREADS) {
             const unsigned s = S.list[li];
             if (S.tag[s] == TAG_DEAD) continue;
@@ -591,7 +637,28 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
                 else atomicAdd(P.edge_counting + (c < 65535u ? c : 65535u), 1ull);
             }
             const unsigned mult = P.threshold ? (c >= P.m ? c : (P.has_assist ? S.acnt[s] : 0u)) : c;
-            if (mult && P.emit) S.emit[atomicAdd(&s_nemit, 1u)] = (uint16_t)s;
+            if (mult && P.emit) ++my_rows;
+        }
+        unsigned row0;
+        {
+            const unsigned lane = tid & 31, warp = tid >> 5;
+            unsigned x = my_rows;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= (unsigned)o) x += y;
+            }
+            if (lane == 31) s_wsum[warp] = x;
+            __syncthreads();
+            unsigned add = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < COUNT_THREADS / 32; ++w) {
+                const unsigned v = s_wsum[w];
+                if ((unsigned)w < warp) add += v;
+                total += v;
+            }
+            row0 = x - my_rows + add;
+            if (tid == 0) s_nemit = total;
         }
         __syncthreads();
         const unsigned ne = s_nemit;
@@ -603,15 +670,19 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
             }
             __syncthreads();
             const unsigned long long eb = s_ebase;
-            if (eb + ne <= P.edges_cap) {
-                for (unsigned j = tid; j < ne; j += COUNT_THREADS) {
-                    const unsigned s = S.emit[j];
+            if (eb + ne <= P.edges_cap && my_rows) {
+                unsigned long long r = eb + row0;
+                for (unsigned li = tid; li < nd; li += COUNT_THREADS) {
+                    const unsigned s = S.list[li];
+                    if (S.tag[s] == TAG_DEAD) continue;
                     const unsigned c = S.cnt[s];
-                    const unsigned mult = P.threshold ? (c >= P.m ? c : S.acnt[s]) : c;
+                    const unsigned mult = P.threshold ? (c >= P.m ? c : (P.has_assist ? S.acnt[s] : 0u)) : c;
+                    if (!mult) continue;
                     uint32_t key[WE];
 #pragma unroll
                     for (int w = 0; w < WE; ++w) key[w] = S.keys[w * cap + s];
-                    uint32_t *row = P.edges_out + (eb + j) * (WE + 1);
+                    uint32_t *row = P.edges_out + r * (WE + 1);
+                    ++r;
 #pragma unroll
                     for (int w = 0; w < WE; ++w) row[w] = key[w];
                     row[WE] = mult;
@@ -698,8 +769,8 @@ __global__ void k_init_slab_cursors(unsigned long long *cursor, unsigned n, unsi
     if (i < n) cursor[i] = (unsigned long long)i * slab_cap;
 }
 
-__global__ void k_count_positions(const uint64_t *__restrict__ start, uint64_t n_reads, int k, unsigned long long *out) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_count_positions(const uint64_t *__restrict__ start, uint64_t r_begin, uint64_t n_reads, int k, unsigned long long *out) {
+    const uint64_t r = r_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long v = 0;
     if (r < n_reads) {
         const int64_t L = (int64_t)(start[r + 1] - start[r]);
