@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--replicated-scan", action="store_true",
+                    help="N>1: every shard scans ALL reads for its hash range (no item all-to-all); default is the scan-sharded stage 1")
     return ap.parse_args()
 
 
@@ -205,7 +207,10 @@ def main():
         h2d = load_reads() if e2e else 0
         d2h = 0
         if a.m > 1:
-            ctx.stage1()
+            if world > 1 and not a.replicated_scan:
+                shards.stage1_scan_sharded(ctx, n_reads, rank, world, dist, dev)
+            else:
+                ctx.stage1()
             exchange_edges()
         if e2e:
             nbytes, meta, totals = ctx.stage2(collect="count")
@@ -277,8 +282,9 @@ def main():
         n1, iw1, rows = st1["n_items"], st1["item_words"], st1["n_edges"]
         row_bytes = (st1["key_words"] + 1) * 4
         if n1:
-            kern.append(("s1.k_edge_part", st1["ms_extract"], seq_bytes * max(1, st1["n_batches"]) + n1 * iw1 * 4))
-            kern.append(("s1.k_split", st1["ms_partition"], 2 * n1 * iw1 * 4))
+            sharded = world > 1 and not a.replicated_scan
+            kern.append(("s1.k_edge_part", st1["ms_extract"], (seq_bytes // world if sharded else seq_bytes * max(1, st1["n_batches"])) + n1 * iw1 * 4))
+            kern.append(("s1.k_split", st1["ms_partition"], (4 if sharded else 2) * n1 * iw1 * 4))
             kern.append(("s1.k_count", st1["ms_sort_emit"], n1 * iw1 * 4 + rows * row_bytes))
         n2, iw2 = st2["n_items"], st2["item_words"]
         if n2:
@@ -318,7 +324,10 @@ def main():
                            "edges_per_step": edges, "s1_items": total_items(st1, world, dist, dev, torch),
                            "s2_items": total_items(st2, world, dist, dev, torch),
                            "l2": "inputs larger than L2 (item arrays are GBs per step); no explicit flush",
-                           "sharding": "contiguous lv1-bucket ranges, %d shard(s)" % world, "gen_seconds": gen_s},
+                           "sharding": "contiguous lv1-bucket ranges, %d shard(s)" % world,
+                           "stage1": ("one shard" if world == 1 else "replicated scan, hash-range shards" if a.replicated_scan
+                                      else "scan-sharded: each shard scans 1/N of the reads, NCCL all-to-all of the items by hash owner"),
+                           "gen_seconds": gen_s},
                 "e2e": {"value": edges / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,

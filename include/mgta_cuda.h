@@ -135,6 +135,26 @@ int mgta_edges_local(mgta_ctx *ctx, void **dev, uint64_t *n_rows, int32_t *row_w
 int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t my_offset_rows, void **dev);
 int mgta_edge_hist_device_buffer(mgta_ctx *ctx, void **dev, uint64_t *n_bytes);
 
+/* Scan-sharded stage 1 when world > 1 (the fast path; mgta_stage1 above makes every shard scan ALL reads for its own
+ * hash range instead).  Shard r extracts the canonical (k+1)-mers of reads [read_begin, read_end) only -- the shards'
+ * ranges partition the read set -- binned by the shard that owns their hash range, into `world` send slabs:
+ *   1. mgta_stage1_scan(ctx, read_begin, read_end, slab_items, &needed).  All shards must use the same slab size
+ *      (equal-split all-to-all), so the caller agrees on it: slab_items == 0 only reports in *needed the size this
+ *      shard would like (take the maximum over the shards); otherwise the scan runs and *needed receives the slab
+ *      size it takes to hold everything: *needed > slab_items means a slab overflowed (skewed input) and NO exchange
+ *      is pending -- rescan with the maximum of *needed over the shards, which always fits.
+ *   2. mgta_stage1_exchange_buffers(): send / recv device buffers of world * slab_bytes bytes each; slab d of `send`
+ *      goes to shard d, slab s of `recv` receives from shard s (one equal-split all-to-all: ncclSend/ncclRecv over
+ *      NVLink, torch.distributed.all_to_all_single); send_counts[d] = items in slab d (all-to-all these too)
+ *   3. mgta_stage1_count(ctx, recv_counts, edge_counting): recv_counts[s] = items shard s sent here; partitions and
+ *      counts the received items exactly like mgta_stage1, leaving this shard's solid-edge rows for the edge exchange
+ *      below.  edge_counting (may be NULL) is this shard's share: sum it over the shards.
+ * Replaces, like mgta_stage1, cx1.run() with the s1 callbacks (build_graph.cpp:100-113). */
+int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t read_end, uint64_t slab_items, uint64_t *needed);
+int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev, uint64_t *slab_bytes,
+                                 uint64_t *send_counts /* [world] */);
+int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts /* [world] */, int64_t *edge_counting);
+
 /* Mercy candidates of this shard (s1.cpp:762-826): packed ((start_idx+kmer_offset)<<2)|flag.
  * Valid after mgta_stage1 with need_mercy.  *n receives the count; copies min(*n, cap). */
 int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t cap, uint64_t *n);

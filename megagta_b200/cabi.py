@@ -39,6 +39,7 @@ SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_
 EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_alloc_reads",
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
+           "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
            "mgta_get_mercy_candidates", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
            "mgta_edge_hist_device_buffer", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version"]
@@ -67,6 +68,12 @@ def load():
         lib.mgta_stage1_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage2_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage1.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_stage1_scan.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.POINTER(ctypes.c_uint64)]
+        lib.mgta_stage1_exchange_buffers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                     ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
+                                                     ctypes.c_void_p]
+        lib.mgta_stage1_count.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_solid_device_buffer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                                  ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_get_is_solid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
@@ -149,6 +156,29 @@ class Context:
     def stage1(self):
         ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
         self._check(self.lib.mgta_stage1(self.h, _p(ec)), "mgta_stage1")
+        return ec
+
+    def stage1_scan(self, read_begin, read_end, slab_items=0):
+        """scan-sharded stage 1, step 1: items of reads [read_begin, read_end) binned by owner shard into send slabs of
+        slab_items items.  slab_items == 0: only report the slab size this shard would like.  Returns the slab size
+        that holds everything; a value above slab_items means "overflow, nothing pending: rescan with at least this"."""
+        need = ctypes.c_uint64()
+        self._check(self.lib.mgta_stage1_scan(self.h, read_begin, read_end, slab_items, ctypes.byref(need)), "mgta_stage1_scan")
+        return need.value
+
+    def stage1_exchange_buffers(self):
+        """-> (send ptr, recv ptr, bytes per slab, items per send slab [world])"""
+        a, b, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64()
+        counts = np.zeros(self.opts.world, dtype=np.uint64)
+        self._check(self.lib.mgta_stage1_exchange_buffers(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n), _p(counts)),
+                    "mgta_stage1_exchange_buffers")
+        return a.value, b.value, n.value, counts
+
+    def stage1_count(self, recv_counts):
+        """scan-sharded stage 1, step 3: count the received items -> this shard's share of edge_counting"""
+        rc = np.ascontiguousarray(recv_counts, dtype=np.uint64)
+        ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
+        self._check(self.lib.mgta_stage1_count(self.h, _p(rc), _p(ec)), "mgta_stage1_count")
         return ec
 
     def get_is_solid(self):

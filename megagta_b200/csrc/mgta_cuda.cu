@@ -37,6 +37,24 @@ struct Timed {
 
 }  // namespace
 
+namespace {
+struct CountPlan {
+    int k, WE, PW, IW, bits;
+    bool plus, has_assist, stage1_mode, mark_mode;
+    unsigned tab_cap, big_cap, tab_limit, lb1, lb2, B1, T, r_lo, r_hi;
+    uint64_t n_pos;
+};
+
+// scan-sharded stage 1 between mgta_stage1_scan and mgta_stage1_count
+struct ExchangeState {
+    bool valid = false;
+    CountPlan cp;
+    uint64_t slab_items = 0;
+    size_t send_off = 0, recv_off = 0, xbytes = 0;      // arena offsets of the send / receive slabs, bytes of each
+    std::vector<uint64_t> send_counts;
+};
+}  // namespace
+
 struct mgta_ctx {
     mgta_opts opt;
     cudaStream_t stream = nullptr;
@@ -77,6 +95,7 @@ struct mgta_ctx {
     int PB = 20;                           // prefix bits of a stage-2 tile: min(20, 2(k-1)), >= 16
     uint64_t n_positions = 0;              // edge offsets over all reads
     bool n_positions_valid = false;
+    ExchangeState xch;
 };
 
 #define CK(call)                                                                                         \
@@ -440,7 +459,7 @@ size_t hbm_budget(mgta_ctx *ctx) {
 int count_positions(mgta_ctx *ctx) {
     if (ctx->n_positions_valid) return MGTA_OK;
     CK(cudaMemsetAsync(ctx->d_totals + 13, 0, 8, ctx->stream));
-    k_count_positions<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_reads, ctx->opt.kmer_k,
+    k_count_positions<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, 0, ctx->n_reads, ctx->opt.kmer_k,
                                                                                      ctx->d_totals + 13);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 13, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -551,229 +570,455 @@ int launch_split(mgta_ctx *ctx, const SplitParams &SP) {
 //   stage-1 mode : marks is_solid, fills edge_counting, lists edges with count >= m (or assist occurrences)
 //   general mode : counts the occurrences the is_solid vector calls solid (no marking), lists every edge
 // Both leave {(canonical edge, multiplicity)} in ctx->d_edges and the stage-2 key-prefix histogram in d_hist_s2.
+//
+// The level-1 hash bins of a batch are filled either by k_edge_part straight from the reads (one GPU, or every shard
+// scanning all reads for its own hash range), or -- scan-sharded exchange, world > 1 -- by k_split (mode 2) from the items
+// the shards sent each other: shard r extracts the items of ITS reads only, binned by owner shard, one all-to-all moves
+// them (mgta_stage1_scan / _exchange_buffers / _count), and everything after the level-1 bins is the same code.
 enum CountMode { CM_STAGE1 = 0, CM_GENERAL = 1, CM_MARK = 2 };
 
-int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
-    const bool stage1_mode = mode != CM_GENERAL;                   // counts every occurrence of this shard's hash range
-    const bool mark_mode = mode == CM_MARK;                        // only (re)derives the is_solid vector
-    const int k = ctx->opt.kmer_k;
+struct CountLay {
+    size_t R, A, B, hist2, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, ovf, total;
+    uint64_t slab_cap, capA, capB;
+    unsigned bins, NT;
+};
+
+int make_count_plan(mgta_ctx *ctx, CountMode mode, CountPlan &cp) {
+    cp.stage1_mode = mode != CM_GENERAL;                           // counts every occurrence of this shard's hash range
+    cp.mark_mode = mode == CM_MARK;                                // only (re)derives the is_solid vector
+    cp.k = ctx->opt.kmer_k;
     int rc = count_positions(ctx);
     if (rc) return rc;
-    const uint64_t n_pos = ctx->n_positions;
-    const int WE = edge_words(k);
-    const bool plus = key_words_s2(k) > WE;
-    const bool has_assist = stage1_mode && ctx->n_short < ctx->n_reads;
+    cp.n_pos = ctx->n_positions;
+    cp.WE = edge_words(cp.k);
+    cp.plus = key_words_s2(cp.k) > cp.WE;
+    cp.has_assist = cp.stage1_mode && ctx->n_short < ctx->n_reads;
     // the base position rides along only when it is needed: to mark is_solid, or to tell assist occurrences apart
-    const int PW = (mark_mode || has_assist) ? (ctx->total_bases >= 0xFFFFFFFEull ? 2 : 1) : 0;
-    const int IW = WE + PW;
-    st->key_words = WE; st->item_words = IW;
-
-    if (!mark_mode) {
-        ctx->edges_valid = false;
-        ctx->edge_row_words = WE + 1;
-    }
-    if (n_pos == 0) {
-        if (!mark_mode) {
-            ctx->n_edges = 0;
-            CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
-            if (stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
-            ctx->edges_valid = true;
-        }
-        return MGTA_OK;
-    }
-
+    cp.PW = (cp.mark_mode || cp.has_assist) ? (ctx->total_bases >= 0xFFFFFFFEull ? 2 : 1) : 0;
+    cp.IW = cp.WE + cp.PW;
     // per-tile table: sized so that two CTAs share an SM; overflow tiles get the largest table that fits one SM
-    const size_t slot_bytes = 4 * (size_t)(2 + (has_assist ? 1 : 0) + WE) + 2;
-    unsigned tab_cap = 4096, big_cap = 16384;
-    while (tab_cap > 1024 && tab_cap * slot_bytes > 106 * 1024) tab_cap >>= 1;       // 2 x (106 KB + static) fit one SM
-    while (big_cap > tab_cap && big_cap * slot_bytes > 200 * 1024) big_cap >>= 1;
-    unsigned tab_limit = tab_cap - 640;                            // COUNT_THREADS inserts may be in flight past the check
-    if (ctx->opt.sort_items_cap > 0) tab_limit = std::min<unsigned>(tab_limit, std::max(8, ctx->opt.sort_items_cap));   // test hook: force the overflow pass
-    // tiles of about tab_cap / 2 items: level-2 fan-out <= 1024, level-1 bins as many as it takes (a batch handles <= 1024)
-    int bits = 2;
+    const size_t slot_bytes = 4 * (size_t)(2 + (cp.has_assist ? 1 : 0) + cp.WE) + 2;
+    cp.tab_cap = 4096; cp.big_cap = 16384;
+    while (cp.tab_cap > 1024 && cp.tab_cap * slot_bytes > 106 * 1024) cp.tab_cap >>= 1;       // 2 x (106 KB + static) fit one SM
+    while (cp.big_cap > cp.tab_cap && cp.big_cap * slot_bytes > 200 * 1024) cp.big_cap >>= 1;
+    cp.tab_limit = cp.tab_cap - 640;                               // COUNT_THREADS inserts may be in flight past the check
+    if (ctx->opt.sort_items_cap > 0) cp.tab_limit = std::min<unsigned>(cp.tab_limit, std::max(8, ctx->opt.sort_items_cap));   // test hook: force the overflow pass
+    // tiles: level-2 fan-out <= 1024, level-1 bins as many as it takes (a batch handles <= 1024).
     // mean tile = up to 3/4 of the table (a Poisson tail of 6 sigma still fits below tab_limit; denser tiles only pay the
     // overflow pass).  Keeping the mean high matters: one more bit doubles the level-1 bins, and past MAX_BINS the reads
     // are scanned once per batch of bins.
-    while (bits < 28 && (n_pos >> bits) > (uint64_t)tab_cap * 3 / 4) ++bits;
-    const unsigned lb2 = (unsigned)std::min(10, bits / 2), lb1 = (unsigned)bits - lb2;
-    const unsigned B1 = 1u << lb1;
-    const unsigned T = split_chunk_items(IW);
-    st->sort_cap = (int)tab_cap;
+    int bits = 2;
+    while (bits < 28 && (cp.n_pos >> bits) > (uint64_t)cp.tab_cap * 3 / 4) ++bits;
+    cp.bits = bits;
+    cp.lb2 = (unsigned)std::min(10, bits / 2);
+    cp.lb1 = (unsigned)bits - cp.lb2;
+    cp.B1 = 1u << cp.lb1;
+    cp.T = split_chunk_items(cp.IW);
+    // this shard's level-1 hash bins (hash ranges balance the shards without a histogram pass)
+    // (the general mode has no exchange step after it, so there every shard counts the whole hash space)
+    cp.r_lo = cp.stage1_mode ? (unsigned)((uint64_t)cp.B1 * ctx->opt.rank / ctx->opt.world) : 0u;
+    cp.r_hi = cp.stage1_mode ? (unsigned)((uint64_t)cp.B1 * (ctx->opt.rank + 1) / ctx->opt.world) : cp.B1;
+    return MGTA_OK;
+}
 
-    const size_t budget = hbm_budget(ctx);
-    double slack = 1.15;
-  for (int attempt = 0;; ++attempt) {          // a level-1 slab overflow restarts the pipeline with slabs sized from what was seen
-    bool retry = false;
-    memset(st, 0, sizeof(*st));
-    st->key_words = WE; st->item_words = IW; st->sort_cap = (int)tab_cap; st->n_giants = (uint64_t)attempt;
-    if (mark_mode) {
+// arena carve for batches of `nb` level-1 bins.  recv_bytes != 0: room for the items received from the other shards
+// (first, at a fixed offset: it must survive a slab-overflow restart); with a single batch it doubles as buffer B.
+void count_layout(const CountPlan &cp, CountLay &L, unsigned nb, double slack, size_t send_bytes, size_t recv_bytes, uint64_t n_recv_cap) {
+    L.bins = (cp.r_hi - cp.r_lo + nb - 1) / nb;
+    L.NT = L.bins << cp.lb2;
+    L.slab_cap = ((uint64_t)((double)cp.n_pos / cp.B1 * slack) + 1024 + 31) & ~(uint64_t)31;
+    L.capA = L.slab_cap * L.bins;
+    uint64_t most = (cp.n_pos + 31) & ~(uint64_t)31;
+    if (recv_bytes) most = std::min<uint64_t>(most, (n_recv_cap + 31) & ~(uint64_t)31);
+    L.capB = std::min<uint64_t>(L.capA, most);
+    Carver c;
+    const size_t bytesA = std::max((size_t)cp.IW * L.capA * 4, send_bytes), bytesB = (size_t)cp.IW * L.capB * 4;
+    if (recv_bytes && nb == 1) { L.B = c.take(std::max(bytesB, recv_bytes)); L.R = L.B; }
+    else if (recv_bytes) { L.R = c.take(recv_bytes); L.B = c.take(bytesB); }
+    else { L.R = 0; L.B = c.take(bytesB); }
+    L.A = c.take(bytesA);
+    L.hist2 = c.take((size_t)L.NT * 4); L.loc = c.take((size_t)L.NT * 4);
+    L.off2 = c.take(((size_t)L.NT + 1) * 8); L.cur2 = c.take((size_t)L.NT * 8);
+    const size_t regions = std::max<size_t>(cp.B1, MAX_OWNERS) + 1;
+    L.tot = c.take(regions * 8); L.base = c.take(regions * 8); L.in_start = c.take(regions * 8);
+    L.chunk_pref = c.take(regions * 4); L.cur1 = c.take(regions * 8);
+    L.ovf = c.take((size_t)L.NT * 4);
+    L.total = c.o;
+}
+
+// grows the arena keeping bytes [0, keep) (the received items of a scan-sharded exchange)
+int ensure_arena_keep(mgta_ctx *ctx, size_t bytes, size_t keep) {
+    if (bytes <= ctx->arena_bytes) return MGTA_OK;
+    if (!keep || !ctx->arena) return ensure_arena(ctx, bytes);
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned char *na = nullptr;
+    CK(cudaMalloc(&na, bytes));
+    CK(cudaMemcpyAsync(na, ctx->arena, std::min(keep, ctx->arena_bytes), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->arena);
+    ctx->arena = na; ctx->arena_bytes = bytes;
+    return MGTA_OK;
+}
+
+// One batch of level-1 bins [b_lo, b_hi) whose slabs (buffer A, cursors cur1) and tile histogram hist2 are filled:
+// exact tile offsets, level-2 split, per-tile hash counting, epilogue.  overflow = a level-1 slab was too small (nothing
+// was counted); need_slack then holds the slack that fits what was seen.
+int count_batch_tail(mgta_ctx *ctx, const CountPlan &cp, const CountLay &L, unsigned b_lo, unsigned b_hi, unsigned n_batches,
+                     unsigned batch, double slack, mgta_stage_stats *st, bool &overflow, double &need_slack) {
+    int rc;
+    overflow = false;
+    const int WE = cp.WE, PW = cp.PW, IW = cp.IW, k = cp.k;
+    uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
+    uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+    unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+    unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
+    const size_t smem_count = count_smem_bytes(WE, cp.tab_cap, cp.has_assist), smem_big = count_smem_bytes(WE, cp.big_cap, cp.has_assist);
+    int occ = 1;
+    // ---- exact tile offsets, K3a: level-2 split
+    ScanParams SP;
+    memset(&SP, 0, sizeof(SP));
+    const unsigned NTb = (b_hi - b_lo) << cp.lb2;
+    SP.hist = hist2; SP.NT = NTb; SP.lb2 = cp.lb2; SP.t_lo = 0; SP.t_hi = NTb;
+    SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
+    SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
+    SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
+    SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
+    SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
+    SP.T = cp.T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
+    SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
+    if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
+    if ((rc = launch_scans(ctx, SP))) return rc;
+    SplitParams XP;
+    memset(&XP, 0, sizeof(XP));
+    XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = IW; XP.WE = WE; XP.mode = 0;
+    XP.sh2 = 32 - cp.bits; XP.lb2 = cp.lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
+    XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
+    if ((rc = launch_split(ctx, XP))) return rc;
+    if ((rc = end_timed(ctx))) return rc;
+    st->n_launches += 4;
+    // ---- K4: per-tile hash counting (edge rows are staged in buffer A, dead after the split)
+    CountParams CP;
+    memset(&CP, 0, sizeof(CP));
+    CP.src = bufB; CP.cap = L.capB; CP.PW = PW; CP.k = k; CP.off2 = off2; CP.t_lo = SP.t_lo; CP.t_hi = SP.t_hi;
+    CP.ticket = ctx->d_ctr + CTR_TICKET2; CP.tab_cap = cp.tab_cap; CP.tab_limit = cp.tab_limit; CP.m = (unsigned)ctx->opt.min_count;
+    CP.mark = cp.mark_mode ? 1 : 0; CP.threshold = cp.stage1_mode ? 1 : 0; CP.has_assist = cp.has_assist ? 1 : 0;
+    CP.emit = cp.mark_mode ? 0 : 1;
+    CP.solid = ctx->d_solid; CP.edge_counting = (cp.stage1_mode && !cp.mark_mode) ? ctx->d_ec : nullptr;
+    CP.edges_out = bufA; CP.n_edges = ctx->d_totals + 14; CP.edges_cap = (uint64_t)IW * L.capA / (WE + 1);
+    CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
+    CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = L.NT;
+    CP.err = ctx->d_ctr + CTR_ERR;
+    if ((rc = begin_timed(ctx, PH_SORT))) return rc;
+    {
+        cudaError_t e = cudaSuccess;
+        WE_SWITCH(WE, {
+            if (cp.plus) {
+                e = cudaFuncSetAttribute(k_count<EE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_count<EE, true>, COUNT_THREADS, smem_count);
+            } else {
+                e = cudaFuncSetAttribute(k_count<EE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_count<EE, false>, COUNT_THREADS, smem_count);
+            }
+        });
+        if (e != cudaSuccess) occ = 1;
+        cudaGetLastError();
+    }
+    if (launch_count(WE, cp.plus, CP, (unsigned)(ctx->sm_count * std::max(1, std::min(occ, 4))), smem_count, ctx->stream))
+        FAIL(MGTA_ERR_CUDA, "k_count launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CountParams CB = CP;                                                             // overflow tiles: one CTA per SM, large table
+    CB.tile_list = CP.ovf_list; CB.n_tile_list = CP.n_ovf; CB.ticket = ctx->d_ctr + CTR_TICKET3;
+    CB.tab_cap = cp.big_cap; CB.tab_limit = cp.big_cap - 1024; CB.ovf_cap = 0; CB.n_ovf = ctx->d_ctr + CTR_NOVF2;
+    if (launch_count(WE, cp.plus, CB, (unsigned)ctx->sm_count, smem_big, ctx->stream))
+        FAIL(MGTA_ERR_CUDA, "k_count (overflow pass) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(cudaGetLastError());
+    if ((rc = end_timed(ctx))) return rc;
+    st->n_launches += 2;
+    // ---- batch epilogue
+    unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+    unsigned long long *h_ne = ctx->h_pin + 2 * NUM_BUCKETS + 8;
+    CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_ne, ctx->d_totals + 14, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_ne + 1, off2 + NTb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned dev_err = h_ctr[CTR_ERR];
+    if (dev_err & ERR_SLAB_OVERFLOW) {                    // this batch was not counted (k_split / k_count bail out)
+        std::vector<unsigned long long> hc(b_hi - b_lo);   // the cursors kept counting past the slab ends: exact bin sizes
+        CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long mx = 0;
+        for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
+        need_slack = std::max(slack * 1.5, (double)mx / ((double)cp.n_pos / cp.B1) * 1.05);
+        overflow = true;
+        return MGTA_OK;
+    }
+    if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (count pipeline, bins [%u,%u))", dev_err, b_lo, b_hi);
+    st->n_items += h_ne[1];
+    st->n_batches++;
+    st->msd_levels = std::max<int>(st->msd_levels, (int)h_ctr[CTR_NOVF]);          // overflow tiles (informational)
+    const uint64_t ne = h_ne[0];
+    if (ne) {
+        const size_t row = (size_t)(WE + 1) * 4;
+        if (ctx->n_edges + ne > ctx->edges_cap) {
+            const uint64_t ncap = std::max<uint64_t>(ctx->n_edges + ne, n_batches > 1 ? (ctx->n_edges + ne) * (n_batches - batch) / 1 : 0);
+            uint32_t *nbuf = nullptr;
+            CK(cudaMalloc(&nbuf, ncap * row));
+            if (ctx->n_edges) CK(cudaMemcpyAsync(nbuf, ctx->d_edges, ctx->n_edges * row, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_edges);
+            ctx->d_edges = nbuf; ctx->edges_cap = ncap;
+        }
+        CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ctx->d_edges) + ctx->n_edges * row, bufA, ne * row, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->n_edges += ne;
+    }
+    return MGTA_OK;
+}
+
+int count_reset_outputs(mgta_ctx *ctx, const CountPlan &cp) {
+    if (cp.mark_mode) {
         CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
     } else {
         ctx->n_edges = 0;
         CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
-        if (stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
+        if (cp.stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
     }
-    unsigned n_batches = 1;
-    struct Lay { size_t A, B, hist2, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, ovf, total; uint64_t slab_cap, capA, capB; unsigned bins; } L;
-    // this shard's level-1 hash bins (hash ranges balance the shards without a histogram pass)
-    // (the general mode has no exchange step after it, so there every shard counts the whole hash space)
-    const unsigned r_lo = stage1_mode ? (unsigned)((uint64_t)B1 * ctx->opt.rank / ctx->opt.world) : 0u;
-    const unsigned r_hi = stage1_mode ? (unsigned)((uint64_t)B1 * (ctx->opt.rank + 1) / ctx->opt.world) : B1;
-    if (r_lo >= r_hi) { if (!mark_mode) ctx->edges_valid = true; return MGTA_OK; }
-    unsigned NT = 0;                                               // tiles of one batch
-    auto layout = [&](unsigned nb) {
-        L.bins = (r_hi - r_lo + nb - 1) / nb;
-        NT = L.bins << lb2;
-        L.slab_cap = ((uint64_t)((double)n_pos / B1 * slack) + 1024 + 31) & ~(uint64_t)31;
-        L.capA = L.slab_cap * L.bins;
-        L.capB = std::min<uint64_t>(L.capA, (n_pos + 31) & ~(uint64_t)31);
-        Carver c;
-        L.A = c.take((size_t)IW * L.capA * 4);
-        L.B = c.take((size_t)IW * L.capB * 4);
-        L.hist2 = c.take((size_t)NT * 4); L.loc = c.take((size_t)NT * 4);
-        L.off2 = c.take(((size_t)NT + 1) * 8); L.cur2 = c.take((size_t)NT * 8);
-        L.tot = c.take((B1 + 1) * 8); L.base = c.take((B1 + 1) * 8); L.in_start = c.take((B1 + 1) * 8);
-        L.chunk_pref = c.take((B1 + 1) * 4); L.cur1 = c.take((B1 + 1) * 8);
-        L.ovf = c.take((size_t)NT * 4);
-        L.total = c.o;
-    };
-    n_batches = (r_hi - r_lo + MAX_BINS - 1) / MAX_BINS;
-    layout(n_batches);
-    while (L.total > budget && L.bins > 1) { n_batches *= 2; layout(n_batches); }
-    if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 hash bin (%zu B)", budget, L.total);
+    return MGTA_OK;
+}
 
-    const size_t smem_count = count_smem_bytes(WE, tab_cap, has_assist), smem_big = count_smem_bytes(WE, big_cap, has_assist);
-    int occ = 1;
-    for (unsigned batch = 0; batch < n_batches; ++batch) {
-        const unsigned b_lo = r_lo + batch * L.bins, b_hi = std::min(r_hi, b_lo + L.bins);
-        if (b_lo >= b_hi) break;
-        {
-            if ((rc = ensure_arena(ctx, L.total))) return rc;
-            uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
-            uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
-            unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
-            unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
-            CK(cudaMemsetAsync(hist2, 0, (size_t)NT * 4, ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_totals + 14, 0, 8, ctx->stream));                      // edge rows written by this batch
-            k_init_slab_cursors<<<(b_hi - b_lo + 255) / 256, 256, 0, ctx->stream>>>(cur1, b_hi - b_lo, L.slab_cap);
-            CK(cudaGetLastError());
+int count_batch_begin(mgta_ctx *ctx, const CountLay &L, unsigned n_bins) {
+    CK(cudaMemsetAsync(ctx->arena + L.hist2, 0, (size_t)L.NT * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_totals + 14, 0, 8, ctx->stream));                      // edge rows written by this batch
+    k_init_slab_cursors<<<(n_bins + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1), n_bins, L.slab_cap);
+    CK(cudaGetLastError());
+    return MGTA_OK;
+}
+
+int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
+    CountPlan cp;
+    int rc = make_count_plan(ctx, mode, cp);
+    if (rc) return rc;
+    const int k = cp.k, WE = cp.WE, PW = cp.PW, IW = cp.IW;
+    st->key_words = WE; st->item_words = IW;
+    if (!cp.mark_mode) {
+        ctx->edges_valid = false;
+        ctx->edge_row_words = WE + 1;
+    }
+    if (cp.n_pos == 0 || cp.r_lo >= cp.r_hi) {
+        if (!cp.mark_mode) {
+            if ((rc = count_reset_outputs(ctx, cp))) return rc;
+            ctx->edges_valid = true;
+        }
+        return MGTA_OK;
+    }
+    st->sort_cap = (int)cp.tab_cap;
+    const size_t budget = hbm_budget(ctx);
+    double slack = 1.15;
+    for (int attempt = 0;; ++attempt) {          // a level-1 slab overflow restarts the pipeline with slabs sized from what was seen
+        bool retry = false;
+        memset(st, 0, sizeof(*st));
+        st->key_words = WE; st->item_words = IW; st->sort_cap = (int)cp.tab_cap; st->n_giants = (uint64_t)attempt;
+        if ((rc = count_reset_outputs(ctx, cp))) return rc;
+        CountLay L;
+        unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
+        count_layout(cp, L, n_batches, slack, 0, 0, 0);
+        while (L.total > budget && L.bins > 1) { n_batches *= 2; count_layout(cp, L, n_batches, slack, 0, 0, 0); }
+        if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 hash bin (%zu B)", budget, L.total);
+        if ((rc = ensure_arena(ctx, L.total))) return rc;
+        for (unsigned batch = 0; batch < n_batches; ++batch) {
+            const unsigned b_lo = cp.r_lo + batch * L.bins, b_hi = std::min(cp.r_hi, b_lo + L.bins);
+            if (b_lo >= b_hi) break;
+            if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) return rc;
             // ---- K1+K2: extraction + level-1 hash partition
             EdgePartParams EP;
             memset(&EP, 0, sizeof(EP));
             EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
             EP.total_bases = ctx->total_bases; EP.k = k;
-            EP.filter = stage1_mode ? 0 : 1; EP.all_solid = ctx->opt.min_count == 1; EP.solid = ctx->d_solid;
-            EP.sh1 = 32 - (int)lb1; EP.sh2 = 32 - bits; EP.lb2 = lb2; EP.b_lo = b_lo; EP.b_hi = b_hi;
-            EP.cursor1 = cur1; EP.slab_cap = L.slab_cap; EP.hist2 = hist2; EP.dst = bufA; EP.cap = L.capA;
+            EP.filter = cp.stage1_mode ? 0 : 1; EP.all_solid = ctx->opt.min_count == 1; EP.solid = ctx->d_solid;
+            EP.sh1 = 32 - (int)cp.lb1; EP.sh2 = 32 - cp.bits; EP.lb2 = cp.lb2; EP.b_lo = b_lo; EP.b_hi = b_hi;
+            EP.cursor1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1); EP.slab_cap = L.slab_cap;
+            EP.hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+            EP.dst = reinterpret_cast<uint32_t *>(ctx->arena + L.A); EP.cap = L.capA;
             EP.err = ctx->d_ctr + CTR_ERR;
             if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
             if (launch_edge_part(WE, PW, EP, ctx->total_bases, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             CK(cudaGetLastError());
             if ((rc = end_timed(ctx))) return rc;
             st->n_launches++;
-            // ---- exact tile offsets, K3a: level-2 split
-            ScanParams SP;
-            memset(&SP, 0, sizeof(SP));
-            const unsigned NTb = (b_hi - b_lo) << lb2;
-            SP.hist = hist2; SP.NT = NTb; SP.lb2 = lb2; SP.t_lo = 0; SP.t_hi = NTb;
-            SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
-            SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
-            SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
-            SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
-            SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
-            SP.T = T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
-            SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
-            if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
-            if ((rc = launch_scans(ctx, SP))) return rc;
-            SplitParams XP;
-            memset(&XP, 0, sizeof(XP));
-            XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = IW; XP.WE = WE; XP.mode = 0;
-            XP.sh2 = 32 - bits; XP.lb2 = lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
-            XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = T; XP.err = ctx->d_ctr + CTR_ERR;
-            if ((rc = launch_split(ctx, XP))) return rc;
-            if ((rc = end_timed(ctx))) return rc;
-            st->n_launches += 4;
-            // ---- K4: per-tile hash counting (edge rows are staged in buffer A, dead after the split)
-            CountParams CP;
-            memset(&CP, 0, sizeof(CP));
-            CP.src = bufB; CP.cap = L.capB; CP.PW = PW; CP.k = k; CP.off2 = off2; CP.t_lo = SP.t_lo; CP.t_hi = SP.t_hi;
-            CP.ticket = ctx->d_ctr + CTR_TICKET2; CP.tab_cap = tab_cap; CP.tab_limit = tab_limit; CP.m = (unsigned)ctx->opt.min_count;
-            CP.mark = mark_mode ? 1 : 0; CP.threshold = stage1_mode ? 1 : 0; CP.has_assist = has_assist ? 1 : 0;
-            CP.emit = mark_mode ? 0 : 1;
-            CP.solid = ctx->d_solid; CP.edge_counting = (stage1_mode && !mark_mode) ? ctx->d_ec : nullptr;
-            CP.edges_out = bufA; CP.n_edges = ctx->d_totals + 14; CP.edges_cap = (uint64_t)IW * L.capA / (WE + 1);
-            CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
-            CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = NT;
-            CP.err = ctx->d_ctr + CTR_ERR;
-            if ((rc = begin_timed(ctx, PH_SORT))) return rc;
-            {
-                cudaError_t e = cudaSuccess;
-                WE_SWITCH(WE, {
-                    if (plus) {
-                        e = cudaFuncSetAttribute(k_count<EE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
-                        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_count<EE, true>, COUNT_THREADS, smem_count);
-                    } else {
-                        e = cudaFuncSetAttribute(k_count<EE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
-                        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_count<EE, false>, COUNT_THREADS, smem_count);
-                    }
-                });
-                if (e != cudaSuccess) occ = 1;
-                cudaGetLastError();
-            }
-            // the occupancy query needs the smem attribute; launch_count sets it (query again is not worth a sync)
-            if (launch_count(WE, plus, CP, (unsigned)(ctx->sm_count * std::max(1, std::min(occ, 4))), smem_count, ctx->stream))
-                FAIL(MGTA_ERR_CUDA, "k_count launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            CountParams CB = CP;                                                             // overflow tiles: one CTA per SM, large table
-            CB.tile_list = CP.ovf_list; CB.n_tile_list = CP.n_ovf; CB.ticket = ctx->d_ctr + CTR_TICKET3;
-            CB.tab_cap = big_cap; CB.tab_limit = big_cap - 1024; CB.ovf_cap = 0; CB.n_ovf = ctx->d_ctr + CTR_NOVF2;
-            if (launch_count(WE, plus, CB, (unsigned)ctx->sm_count, smem_big, ctx->stream))
-                FAIL(MGTA_ERR_CUDA, "k_count (overflow pass) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            CK(cudaGetLastError());
-            if ((rc = end_timed(ctx))) return rc;
-            st->n_launches += 2;
-            // ---- batch epilogue
-            unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
-            unsigned long long *h_ne = ctx->h_pin + 2 * NUM_BUCKETS + 8;
-            CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(h_ne, ctx->d_totals + 14, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(h_ne + 1, off2 + NTb, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            const unsigned dev_err = h_ctr[CTR_ERR];
-            if (dev_err & ERR_SLAB_OVERFLOW) {                    // this batch was not counted (k_split / k_count bail out)
+            bool overflow = false;
+            double need = slack;
+            if ((rc = count_batch_tail(ctx, cp, L, b_lo, b_hi, n_batches, batch, slack, st, overflow, need))) return rc;
+            if (overflow) {
                 if (attempt >= 6) FAIL(MGTA_ERR_MEM, "level-1 hash bins overflow their slabs even with %.1fx slack", slack);
-                std::vector<unsigned long long> hc(b_hi - b_lo);   // the cursors kept counting past the slab ends: exact bin sizes
-                CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
-                unsigned long long mx = 0;
-                for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
-                slack = std::max(slack * 1.5, (double)mx / ((double)n_pos / B1) * 1.05);
+                slack = need;
                 retry = true;
                 break;
             }
-            if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (count pipeline, bins [%u,%u))", dev_err, b_lo, b_hi);
-            st->n_items += h_ne[1];
-            st->n_batches++;
-            st->msd_levels = std::max<int>(st->msd_levels, (int)h_ctr[CTR_NOVF]);          // overflow tiles (informational)
-            const uint64_t ne = h_ne[0];
-            if (ne) {
-                const size_t row = (size_t)(WE + 1) * 4;
-                if (ctx->n_edges + ne > ctx->edges_cap) {
-                    const uint64_t ncap = std::max<uint64_t>(ctx->n_edges + ne, n_batches > 1 ? (ctx->n_edges + ne) * (n_batches - batch) / 1 : 0);
-                    uint32_t *nbuf = nullptr;
-                    CK(cudaMalloc(&nbuf, ncap * row));
-                    if (ctx->n_edges) CK(cudaMemcpyAsync(nbuf, ctx->d_edges, ctx->n_edges * row, cudaMemcpyDeviceToDevice, ctx->stream));
-                    CK(cudaStreamSynchronize(ctx->stream));
-                    cudaFree(ctx->d_edges);
-                    ctx->d_edges = nbuf; ctx->edges_cap = ncap;
-                }
-                CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ctx->d_edges) + ctx->n_edges * row, bufA, ne * row, cudaMemcpyDeviceToDevice, ctx->stream));
-                ctx->n_edges += ne;
+        }
+        if (!retry) break;
+    }
+    if (cp.mark_mode) ctx->solid_valid = true; else ctx->edges_valid = true;
+    return MGTA_OK;
+}
+
+// ---- scan-sharded stage 1 (world > 1): scan, [caller: all-to-all], count ---------------------------------------------
+int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab_in, uint64_t *needed, mgta_stage_stats *st) {
+    ExchangeState &X = ctx->xch;
+    X.valid = false;
+    if (r_begin > r_end || r_end > ctx->n_reads) FAIL(MGTA_ERR_ARG, "stage1_scan: bad read range");
+    const int world = ctx->opt.world;
+    if (world > MAX_OWNERS) FAIL(MGTA_ERR_ARG, "stage1_scan: at most %d shards", (int)MAX_OWNERS);
+    CountPlan cp;
+    int rc = make_count_plan(ctx, CM_STAGE1, cp);
+    if (rc) return rc;
+    st->key_words = cp.WE; st->item_words = cp.IW; st->sort_cap = (int)cp.tab_cap;
+    ctx->edges_valid = false;
+    ctx->edge_row_words = cp.WE + 1;
+    // edge offsets of the local reads, base range of the scan
+    uint64_t n_local = 0, g_begin = 0, g_end = 0;
+    if (r_begin < r_end) {
+        CK(cudaMemsetAsync(ctx->d_totals + 13, 0, 8, ctx->stream));
+        k_count_positions<<<(unsigned)((r_end - r_begin + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, r_begin, r_end, cp.k, ctx->d_totals + 13);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 13, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pin + 1, ctx->d_start + r_begin, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pin + 2, ctx->d_start + r_end, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_local = ctx->h_pin[0]; g_begin = ctx->h_pin[1]; g_end = ctx->h_pin[2];
+    }
+    std::vector<unsigned> owner_lo(world + 1);
+    for (int d = 0; d <= world; ++d) owner_lo[d] = (unsigned)((uint64_t)cp.B1 * d / world);
+    const size_t budget = hbm_budget(ctx);
+    // send slabs: hash ranges are balanced, so a slab is the mean share plus a small margin.  All shards must use the
+    // same slab size (equal-split all-to-all), so the caller agrees on it: slab_in == 0 only reports the size this shard
+    // would like; the cursors keep counting past a full slab, so a skewed input (one k-mer dominating) reports the exact
+    // size that fits and costs one rescan.
+    if (slab_in == 0) {
+        *needed = ((uint64_t)((double)n_local / world * 1.02) + 4096 + 31) & ~(uint64_t)31;
+        return MGTA_OK;
+    }
+    const uint64_t slab_items = (slab_in + 31) & ~(uint64_t)31;
+    {
+        const size_t xbytes = (size_t)world * cp.IW * slab_items * 4;
+        // the count phase's arena layout, sized for the worst case this shard can receive
+        unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
+        if (cp.r_hi <= cp.r_lo) n_batches = 1;
+        CountLay L;
+        count_layout(cp, L, n_batches, 1.15, xbytes, xbytes, (uint64_t)world * slab_items);
+        if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the scan-sharded exchange (%zu B)", budget, L.total);
+        if ((rc = ensure_arena(ctx, L.total))) return rc;
+        uint32_t *send = reinterpret_cast<uint32_t *>(ctx->arena + L.A);
+        unsigned long long *cur = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+        const unsigned long long stride = (unsigned long long)cp.IW * slab_items;
+        CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+        k_init_slab_cursors<<<1, 256, 0, ctx->stream>>>(cur, (unsigned)world, stride);
+        CK(cudaGetLastError());
+        if (g_begin < g_end) {
+            EdgePartParams EP;
+            memset(&EP, 0, sizeof(EP));
+            EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
+            EP.total_bases = ctx->total_bases; EP.k = cp.k; EP.filter = 0; EP.all_solid = 0; EP.solid = ctx->d_solid;
+            EP.sh1 = 32 - (int)cp.lb1; EP.sh2 = 32 - cp.bits; EP.lb2 = cp.lb2; EP.b_lo = 0; EP.b_hi = cp.B1;
+            EP.cursor1 = cur; EP.slab_cap = slab_items; EP.slab_stride = stride; EP.hist2 = nullptr;
+            EP.dst = send; EP.cap = slab_items; EP.err = ctx->d_ctr + CTR_ERR;
+            EP.n_owner = world;
+            for (int d = 0; d <= world; ++d) EP.owner_lo[d] = owner_lo[d];
+            EP.g_begin = g_begin & ~(uint64_t)1023; EP.g_end = g_end; EP.r_begin = r_begin;
+            if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
+            if (launch_edge_part(cp.WE, cp.PW, EP, g_end - EP.g_begin, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            if ((rc = end_timed(ctx))) return rc;
+            st->n_launches++;
+        }
+        unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+        CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pin, cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        X.send_counts.assign(world, 0);
+        uint64_t mx = 0;
+        for (int d = 0; d < world; ++d) { X.send_counts[d] = ctx->h_pin[d] - (unsigned long long)d * stride; mx = std::max(mx, X.send_counts[d]); }
+        const unsigned dev_err = h_ctr[CTR_ERR];
+        *needed = std::max<uint64_t>(slab_items, (mx + 31) & ~(uint64_t)31);
+        if (dev_err & ERR_SLAB_OVERFLOW) { st->n_giants++; return MGTA_OK; }         // *needed > slab: the caller rescans
+        if (dev_err & ~(unsigned)ERR_SLAB_OVERFLOW) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage1_scan)", dev_err);
+        X.cp = cp; X.slab_items = slab_items; X.send_off = L.A; X.recv_off = L.R; X.xbytes = xbytes;
+        X.valid = true;
+        return MGTA_OK;
+    }
+}
+
+int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats *st) {
+    ExchangeState &X = ctx->xch;
+    if (!X.valid) FAIL(MGTA_ERR_STATE, "stage1_count: call mgta_stage1_scan (and exchange the items) first");
+    X.valid = false;
+    const CountPlan &cp = X.cp;
+    const int world = ctx->opt.world;
+    int rc;
+    uint64_t n_recv = 0;
+    for (int s = 0; s < world; ++s) {
+        if (recv_counts[s] > X.slab_items) FAIL(MGTA_ERR_ARG, "stage1_count: shard %d sent %llu items, a slab holds %llu", s,
+                                                (unsigned long long)recv_counts[s], (unsigned long long)X.slab_items);
+        n_recv += recv_counts[s];
+    }
+    if ((rc = count_reset_outputs(ctx, cp))) return rc;
+    if (n_recv == 0 || cp.r_lo >= cp.r_hi) { ctx->edges_valid = true; return MGTA_OK; }
+    // input regions of the level-1 split = the slabs received from the shards
+    std::vector<unsigned long long> in_start(world + 1, 0), in_count(world + 1, 0);
+    std::vector<unsigned> chunk_pref(world + 1, 0);
+    for (int s = 0; s < world; ++s) {
+        in_start[s] = (unsigned long long)s * cp.IW * X.slab_items;
+        in_count[s] = recv_counts[s];
+        chunk_pref[s + 1] = chunk_pref[s] + (unsigned)((recv_counts[s] + cp.T - 1) / cp.T);
+    }
+    unsigned long long *d_xs = nullptr;                            // [in_start | in_count | chunk_pref]: 3 small arrays
+    CK(cudaMalloc(&d_xs, (size_t)(world + 1) * 24));
+    auto free_xs = [&]() { cudaFree(d_xs); };
+    cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    const size_t budget = hbm_budget(ctx);
+    double slack = 1.15;
+    for (int attempt = 0;; ++attempt) {
+        bool retry = false;
+        const uint64_t giants0 = st->n_giants;
+        st->n_items = 0; st->n_batches = 0;
+        if ((rc = count_reset_outputs(ctx, cp))) { free_xs(); return rc; }
+        CountLay L;
+        unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
+        count_layout(cp, L, n_batches, slack, X.xbytes, X.xbytes, (uint64_t)world * X.slab_items);
+        if (L.R != X.recv_off) { free_xs(); FAIL(MGTA_ERR_INTERNAL, "stage1_count: receive buffer moved"); }
+        if (L.total > budget) { free_xs(); FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the level-1 slabs (%zu B)", budget, L.total); }
+        if ((rc = ensure_arena_keep(ctx, L.total, X.recv_off + X.xbytes))) { free_xs(); return rc; }
+        for (unsigned batch = 0; batch < n_batches; ++batch) {
+            const unsigned b_lo = cp.r_lo + batch * L.bins, b_hi = std::min(cp.r_hi, b_lo + L.bins);
+            if (b_lo >= b_hi) break;
+            if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) { free_xs(); return rc; }
+            SplitParams XP;
+            memset(&XP, 0, sizeof(XP));
+            XP.src = reinterpret_cast<uint32_t *>(ctx->arena + L.R); XP.dst = reinterpret_cast<uint32_t *>(ctx->arena + L.A);
+            XP.cap_src = X.slab_items; XP.cap_dst = L.capA; XP.IW = cp.IW; XP.WE = cp.WE; XP.mode = 2;
+            XP.sh1 = 32 - (int)cp.lb1; XP.sh2 = 32 - cp.bits; XP.lb2 = cp.lb2;
+            XP.in_start = d_xs; XP.in_count = d_xs + (world + 1); XP.chunk_pref = reinterpret_cast<unsigned *>(d_xs + 2 * (world + 1));
+            XP.B1 = (unsigned)world; XP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+            XP.ticket = ctx->d_ctr + CTR_NLIST0; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
+            XP.b_lo = b_lo; XP.b_hi = b_hi; XP.slab_cap = L.slab_cap; XP.hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+            if ((rc = begin_timed(ctx, PH_PARTITION))) { free_xs(); return rc; }
+            if ((rc = launch_split(ctx, XP))) { free_xs(); return rc; }
+            if ((rc = end_timed(ctx))) { free_xs(); return rc; }
+            st->n_launches++;
+            bool overflow = false;
+            double need = slack;
+            if ((rc = count_batch_tail(ctx, cp, L, b_lo, b_hi, n_batches, batch, slack, st, overflow, need))) { free_xs(); return rc; }
+            if (overflow) {
+                if (attempt >= 6) { free_xs(); FAIL(MGTA_ERR_MEM, "level-1 hash bins overflow their slabs even with %.1fx slack", slack); }
+                slack = need;
+                st->n_giants = giants0 + 1;
+                retry = true;
+                break;
             }
         }
+        if (!retry) break;
     }
-    if (!retry) break;
-  }
-    if (mark_mode) ctx->solid_valid = true; else ctx->edges_valid = true;
+    free_xs();
+    ctx->edges_valid = true;
     return MGTA_OK;
 }
 
@@ -1118,6 +1363,54 @@ extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
         for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
     }
     return stage_end(ctx, st, tm);
+}
+
+extern "C" int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t read_end, uint64_t slab_items, uint64_t *needed) {
+    if (!ctx || !needed) return MGTA_ERR_ARG;
+    if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
+    if (ctx->opt.min_count == 1) FAIL(MGTA_ERR_STATE, "stage1_scan: min_count == 1 has no stage 1");
+    if (ctx->opt.need_mercy) FAIL(MGTA_ERR_ARG, "need_mercy is not implemented on the device yet");
+    if (ctx->n_short < ctx->n_reads) FAIL(MGTA_ERR_ARG, "stage1_scan: assist reads take the replicated scan (mgta_stage1)");
+    mgta_stage_stats *st = &ctx->stats[0];
+    StageTimer tm;
+    int rc = stage_begin(ctx, st, tm);
+    if (rc) return rc;
+    ctx->solid_valid = false;
+    ctx->stage1_done = false;
+    if ((rc = exchange_scan(ctx, read_begin, read_end, slab_items, needed, st))) return rc;
+    return stage_end(ctx, st, tm);
+}
+
+extern "C" int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev, uint64_t *slab_bytes,
+                                            uint64_t *send_counts) {
+    if (!ctx || !send_dev || !recv_dev || !slab_bytes || !send_counts) return MGTA_ERR_ARG;
+    if (!ctx->xch.valid) FAIL(MGTA_ERR_STATE, "no exchange pending: call mgta_stage1_scan first");
+    *send_dev = ctx->arena + ctx->xch.send_off;
+    *recv_dev = ctx->arena + ctx->xch.recv_off;
+    *slab_bytes = (uint64_t)ctx->xch.cp.IW * ctx->xch.slab_items * 4;
+    for (int d = 0; d < ctx->opt.world; ++d) send_counts[d] = ctx->xch.send_counts[d];
+    return MGTA_OK;
+}
+
+extern "C" int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts, int64_t *edge_counting) {
+    if (!ctx || !recv_counts) return MGTA_ERR_ARG;
+    mgta_stage_stats scan = ctx->stats[0], *st = &ctx->stats[0];
+    StageTimer tm;
+    int rc = stage_begin(ctx, st, tm);
+    if (rc) return rc;
+    st->key_words = scan.key_words; st->item_words = scan.item_words; st->sort_cap = scan.sort_cap;
+    if ((rc = exchange_count(ctx, recv_counts, st))) return rc;
+    ctx->stage1_done = true;
+    st->n_edges = ctx->n_edges;
+    if (edge_counting) {
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
+    }
+    if ((rc = stage_end(ctx, st, tm))) return rc;
+    st->ms_total += scan.ms_total; st->ms_extract += scan.ms_extract; st->n_launches += scan.n_launches;
+    st->n_giants += scan.n_giants;
+    return MGTA_OK;
 }
 
 extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals) {

@@ -47,6 +47,46 @@ def exchange(rank, world, dist, device, n_local, row_words, reserve, hist):
     return counts, offs
 
 
+def read_range(n_reads, rank, world):
+    """reads [begin, end) that shard `rank` scans in the scan-sharded stage 1: equal contiguous slices"""
+    return n_reads * rank // world, n_reads * (rank + 1) // world
+
+
+def agree_max(value, dist, device):
+    t = torch.as_tensor([int(value)], dtype=torch.int64).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+def exchange_items(rank, world, dist, device, send, recv, send_counts):
+    """All-to-all of the stage-1 items between the scan and the count step.  send / recv: int32 tensors of `world`
+    equal slabs (slab d of `send` goes to shard d, slab s of `recv` comes from shard s); send_counts: items per send
+    slab.  Returns the items received from every shard (list of world ints)."""
+    sc = torch.as_tensor([int(x) for x in send_counts], dtype=torch.int64).to(device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc)
+    dist.all_to_all_single(recv, send)
+    return [int(x) for x in rc.tolist()]
+
+
+def stage1_scan_sharded(ctx, n_reads, rank, world, dist, device):
+    """Scan-sharded stage 1 over a cabi.Context: scan my slice of the reads, all-to-all the items over NCCL, count.
+    Returns this shard's share of edge_counting (numpy int64[65536])."""
+    lo, hi = read_range(n_reads, rank, world)
+    slab = agree_max(ctx.stage1_scan(lo, hi, 0), dist, device)
+    need = agree_max(ctx.stage1_scan(lo, hi, slab), dist, device)
+    if need > slab:                                   # a send slab overflowed somewhere (skewed input): one rescan that fits
+        slab = need
+        need = agree_max(ctx.stage1_scan(lo, hi, slab), dist, device)
+        if need > slab:
+            raise RuntimeError("stage-1 send slabs overflow after the rescan")
+    sp, rp, slab_bytes, counts = ctx.stage1_exchange_buffers()
+    send = torch.as_tensor(DevBuf(sp, world * slab_bytes), device=device)
+    recv = torch.as_tensor(DevBuf(rp, world * slab_bytes), device=device)
+    got = exchange_items(rank, world, dist, device, send, recv, counts)
+    return ctx.stage1_count(got)
+
+
 def exchange_ctx(ctx, rank, world, dist, device):
     """The same over a cabi.Context (device pointers from the C ABI)."""
     _, n, w = ctx.edges_local()

@@ -4,7 +4,7 @@
         tests/gpu_multi.py [case ...]
 
 One process per GPU over NCCL, exactly the call chain bench.py times: rank 0 uploads the packed reads, ncclBroadcast
-to the other ranks, hash-sharded stage 1, exchange of the solid-edge rows + stage-2 prefix histogram, bucket-sharded
+to the other ranks, scan-sharded stage 1 (items all-to-all by hash owner), exchange of the solid-edge rows + stage-2 prefix histogram, bucket-sharded
 stage 2.  The shard streams are concatenated in rank order (= bucket order) on rank 0 and compared with the goldens
 the UNMODIFIED reference binary produced (tests/golden/golden.json): stream hash, per-bucket table hash, w totals and
 the .counting text."""
@@ -62,7 +62,10 @@ def main():
             dist.broadcast(torch.as_tensor(shards.DevBuf(tp, tb), device=dev), 0)
             ec = torch.zeros(65536, dtype=torch.int64, device=dev)
             if m > 1:
-                ec = torch.from_numpy(ctx.stage1()).to(dev)
+                if os.environ.get("MGTA_REPLICATED_SCAN"):   # legacy: every shard scans all reads for its hash range
+                    ec = torch.from_numpy(ctx.stage1()).to(dev)
+                else:                                        # scan-sharded: scan my reads, all-to-all the items, count
+                    ec = torch.from_numpy(shards.stage1_scan_sharded(ctx, n_reads, rank, world, dist, dev)).to(dev)
                 shards.exchange_ctx(ctx, rank, world, dist, dev)
                 dist.all_reduce(ec)
             st, meta, totals = ctx.stage2()
