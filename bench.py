@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--root-upload", action="store_true",
+                    help="N>1: rank 0 uploads all reads and broadcasts them (default: every rank uploads its slice, NCCL all-gather)")
     ap.add_argument("--replicated-scan", action="store_true",
                     help="N>1: every shard scans ALL reads for its hash range (no item all-to-all); default is the scan-sharded stage 1")
     return ap.parse_args()
@@ -115,31 +117,68 @@ def run_reference_arm(a):
 
 # ------------------------------------------------------------------------------------------------ our arm
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU during the timed region.  NVML in-process (pynvml): spawning nvidia-smi
+    ten times a second measurably slows a step that synchronises with the host often (2-GPU step 246 -> 304 ms);
+    nvidia-smi remains the fallback when the binding is missing."""
+    REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+
     def __init__(self, dev):
         super().__init__(daemon=True)
-        self.dev, self.stop_flag, self.rows = dev, False, []
+        self.dev, self.stop_flag, self.rows, self.max_mhz, self.source = dev, False, [], None, "nvidia-smi"
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = self.handle = None
 
-    def run(self):
+    def sample_nvml(self):
+        n = self.nvml
+        sm = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((sm, mask))
+
+    def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        if o:
+            f = [x.strip() for x in o.split(",")]
+            if f[0].isdigit():
+                if f[1].isdigit():
+                    self.max_mhz = int(f[1])
+                mask = sum(bit for (bit, _), v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active"))
+                self.rows.append((int(f[0]), mask))
+
+    def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nvml:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nvml else 0.5)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [name for bit, name in self.REASONS if any(r[1] & bit for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows),
+                "source": self.source}
 
 
 class DevBuf:
@@ -171,27 +210,52 @@ def main():
     work = tempfile.mkdtemp(prefix="mgta_bench_")
     sample_prefix, sample_n = os.path.join(work, "sample"), auto_sample(a)
     n_words = n_reads * L // 16 + 1
-    if rank == 0:
-        t0 = time.time()
+    # N = 1 (or --root-upload): rank 0 holds all reads, uploads them and broadcasts.  N > 1: every rank holds ITS slice of the
+    # read set in pinned host memory (as if it had read its part of the .bin file), uploads it over its own PCIe link into
+    # place in the full device buffer, and one NCCL all-gather over NVLink completes the buffers on every GPU.
+    sharded_upload = world > 1 and not a.root_upload
+    per_words = a.reads_per_gpu * L // 16                      # words of one shard's slice (reads_per_gpu * L % 16 == 0)
+    assert not sharded_upload or (a.reads_per_gpu * L) % 16 == 0 and a.reads_per_gpu % 1_000_000 == 0
+    t0 = time.time()
+    if sharded_upload:
+        seq, start = synth.packed_metagenome(a.reads_per_gpu, L, seed=a.seed, first_read=rank * a.reads_per_gpu,
+                                             bin_prefix=sample_prefix if rank == 0 else None, bin_reads=sample_n if rank == 0 else 0,
+                                             procs=max(1, (os.cpu_count() or 8) // world))
+        seq_pin = torch.from_numpy(seq[:per_words].view(np.int32)).pin_memory()
+        start_pin = torch.from_numpy((start[:a.reads_per_gpu] + np.uint64(rank * a.reads_per_gpu * L)).view(np.int64)).pin_memory()
+        del seq, start
+    elif rank == 0:
         seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix, bin_reads=sample_n)
         seq_pin = torch.from_numpy(seq).pin_memory()
         start_pin = torch.from_numpy(start.view(np.int64)).pin_memory()
         del seq, start
-        gen_s = time.time() - t0
+    gen_s = time.time() - t0
     stream = torch.cuda.Stream(device=dev)
     ctx = cabi.Context(a.k, a.m, device=local, rank=rank, world=world, stream=stream.cuda_stream)
 
     def load_reads():
-        """host -> HBM (+ broadcast).  Returns H2D bytes."""
+        """host -> HBM (+ all-gather / broadcast over NVLink).  Returns H2D bytes of this rank."""
         h2d = 0
-        if rank == 0:
+        if sharded_upload:
+            ctx.alloc_reads(n_words, n_reads, n_reads, n_reads * L, L)
+            (sp, sb), (tp, tb) = ctx.reads_device_buffers()
+            d_seq = torch.as_tensor(DevBuf(sp, world * per_words * 4), device=dev)             # the last (+1) word stays zero
+            d_start = torch.as_tensor(DevBuf(tp, n_reads * 8, "<i8", 8), device=dev)
+            d_seq[rank * per_words:(rank + 1) * per_words].copy_(seq_pin, non_blocking=True)
+            d_start[rank * a.reads_per_gpu:(rank + 1) * a.reads_per_gpu].copy_(start_pin, non_blocking=True)
+            dist.all_gather_into_tensor(d_seq, d_seq[rank * per_words:(rank + 1) * per_words])
+            dist.all_gather_into_tensor(d_start, d_start[rank * a.reads_per_gpu:(rank + 1) * a.reads_per_gpu])
+            torch.as_tensor(DevBuf(tp + n_reads * 8, 8, "<i8", 8), device=dev).fill_(n_reads * L)   # start_idx[n_reads]
+            torch.as_tensor(DevBuf(sp + world * per_words * 4, 4), device=dev).fill_(0)             # the spare last word
+            h2d = per_words * 4 + a.reads_per_gpu * 8
+        elif rank == 0:
             ctx._check(ctx.lib.mgta_set_reads(ctx.h, seq_pin.data_ptr(), n_words, start_pin.data_ptr(), n_reads, n_reads, L),
                        "mgta_set_reads")
             ctx.n_short, ctx.max_len = n_reads, L
             h2d = n_words * 4 + (n_reads + 1) * 8
         else:
             ctx.alloc_reads(n_words, n_reads, n_reads, n_reads * L, L)
-        if world > 1:
+        if world > 1 and not sharded_upload:
             (sp, sb), (tp, tb) = ctx.reads_device_buffers()
             dist.broadcast(torch.as_tensor(DevBuf(sp, sb), device=dev), 0)
             dist.broadcast(torch.as_tensor(DevBuf(tp, tb), device=dev), 0)
@@ -327,6 +391,8 @@ def main():
                            "sharding": "contiguous lv1-bucket ranges, %d shard(s)" % world,
                            "stage1": ("one shard" if world == 1 else "replicated scan, hash-range shards" if a.replicated_scan
                                       else "scan-sharded: each shard scans 1/N of the reads, NCCL all-to-all of the items by hash owner"),
+                           "upload": ("rank 0 H2D" + (" + NCCL broadcast" if world > 1 else "") if not sharded_upload
+                                      else "every rank H2D of its slice + NCCL all-gather"),
                            "gen_seconds": gen_s},
                 "e2e": {"value": edges / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

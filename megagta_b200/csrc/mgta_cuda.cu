@@ -87,6 +87,10 @@ struct mgta_ctx {
     // stage-2 items they generate by PB-bit key prefix
     uint32_t *d_edges = nullptr;
     uint64_t n_edges = 0, edges_cap = 0;
+    uint32_t *d_edges_all = nullptr;       // world > 1: the rows of all shards (mgta_edges_reserve); kept across steps
+    uint64_t n_edges_all = 0, edges_all_cap = 0;
+    bool edges_all_valid = false;
+    unsigned long long *d_xs = nullptr;    // scan-sharded exchange: input regions of the level-1 split
     int edge_row_words = 0;
     bool edges_valid = false;
     bool solid_valid = false;              // d_solid holds the is_solid vector of the last stage 1 (derived on demand)
@@ -267,6 +271,7 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_ctr, CTR_COUNT * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     ctx->PB = std::min(20, 2 * (opts->kmer_k - 1));
     if ((e = cudaMalloc(&ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_xs, (size_t)(MAX_OWNERS + 1) * 24)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     *out = ctx;
     return MGTA_OK;
@@ -279,6 +284,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
+    cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -306,9 +312,11 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     ctx->n_words = n_words; ctx->n_reads = n_reads; ctx->n_short = n_short; ctx->total_bases = total;
     ctx->max_len = max_len;
     ctx->edges_valid = false;
+    ctx->edges_all_valid = false;
     ctx->solid_valid = false;
     ctx->stage1_done = false;
     ctx->n_positions_valid = false;
+    ctx->xch.valid = false;
     return MGTA_OK;
 }
 }  // namespace
@@ -777,6 +785,7 @@ int count_reset_outputs(mgta_ctx *ctx, const CountPlan &cp) {
         CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
     } else {
         ctx->n_edges = 0;
+        ctx->edges_all_valid = false;
         CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
         if (cp.stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
     }
@@ -968,9 +977,8 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
         in_count[s] = recv_counts[s];
         chunk_pref[s + 1] = chunk_pref[s] + (unsigned)((recv_counts[s] + cp.T - 1) / cp.T);
     }
-    unsigned long long *d_xs = nullptr;                            // [in_start | in_count | chunk_pref]: 3 small arrays
-    CK(cudaMalloc(&d_xs, (size_t)(world + 1) * 24));
-    auto free_xs = [&]() { cudaFree(d_xs); };
+    unsigned long long *d_xs = ctx->d_xs;                          // [in_start | in_count | chunk_pref]: 3 small arrays
+    auto free_xs = [&]() {};
     cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -1158,11 +1166,12 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         // ---- K2': items of the distinct edges, level-1 prefix partition
         ItemPartParams IP;
         memset(&IP, 0, sizeof(IP));
-        IP.edges = ctx->d_edges; IP.n_edges = ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
+        IP.edges = ctx->edges_all_valid ? ctx->d_edges_all : ctx->d_edges;
+        IP.n_edges = ctx->edges_all_valid ? ctx->n_edges_all : ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
         IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = B1; IP.dst = bufA; IP.cap = pl.cap;
         IP.err = ctx->d_ctr + CTR_ERR;
         if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
-        if (launch_item_part(WE, plus, IP, (unsigned)((ctx->n_edges + ITEM_EDGES - 1) / ITEM_EDGES), ctx->stream))
+        if (launch_item_part(WE, plus, IP, (unsigned)((IP.n_edges + ITEM_EDGES - 1) / ITEM_EDGES), ctx->stream))
             FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         CK(cudaGetLastError());
         if ((rc = end_timed(ctx))) return rc;
@@ -1489,6 +1498,7 @@ extern "C" int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(tmp);
     ctx->edges_valid = false;
+    ctx->edges_all_valid = false;
     ctx->solid_valid = true;
     return MGTA_OK;
 }
@@ -1513,15 +1523,21 @@ extern "C" int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t
     if (my_offset_rows + ctx->n_edges > n_rows_total) FAIL(MGTA_ERR_ARG, "edges_reserve: local rows do not fit at that offset");
     CK(cudaSetDevice(ctx->opt.device));
     const size_t row = (size_t)ctx->edge_row_words * 4;
-    uint32_t *nbuf = nullptr;
-    CK(cudaMalloc(&nbuf, std::max<size_t>(n_rows_total * row, 256)));
+    if (n_rows_total > ctx->edges_all_cap || !ctx->d_edges_all) {  // grows only: no allocation on the steady-state path
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_edges_all);
+        ctx->d_edges_all = nullptr; ctx->edges_all_cap = 0;
+        const uint64_t ncap = n_rows_total + n_rows_total / 16 + 64;
+        CK(cudaMalloc(&ctx->d_edges_all, ncap * row));
+        ctx->edges_all_cap = ncap;
+    }
     if (ctx->n_edges)
-        CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(nbuf) + my_offset_rows * row, ctx->d_edges, ctx->n_edges * row,
+        CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ctx->d_edges_all) + my_offset_rows * row, ctx->d_edges, ctx->n_edges * row,
                            cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_edges);
-    ctx->d_edges = nbuf; ctx->edges_cap = n_rows_total; ctx->n_edges = n_rows_total;
-    *dev = nbuf;
+    ctx->n_edges_all = n_rows_total;
+    ctx->edges_all_valid = true;
+    *dev = ctx->d_edges_all;
     return MGTA_OK;
 }
 

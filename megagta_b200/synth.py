@@ -122,18 +122,20 @@ def _chunk_packed(args):
 
 
 def packed_metagenome(n_reads, read_len, seed=20261017, n_genomes=64, glen=(200_000, 2_000_000), sigma=1.5, err=0.01,
-                      procs=None, bin_prefix=None, bin_reads=0, chunk=1_000_000):
+                      procs=None, bin_prefix=None, bin_reads=0, chunk=1_000_000, first_read=0):
     """In-memory reads as the reference holds them (reversed, bit-contiguous): -> (seq u32[], start u64[n+1]).
     Optionally also writes the first `bin_reads` reads as a reference read library at `bin_prefix`
-    (the bounded sample the CPU baseline runs on)."""
+    (the bounded sample the CPU baseline runs on).  first_read (a multiple of `chunk`): generate reads
+    [first_read, first_read + n_reads) of the same stream -- every chunk has its own RNG stream, so the slices the shards
+    generate concatenate to exactly the read set one process would generate."""
     import multiprocessing as mp
     import os
-    assert (chunk * read_len) % 16 == 0
+    assert (chunk * read_len) % 16 == 0 and first_read % chunk == 0
     procs = procs or min(32, os.cpu_count() or 1)
     jobs = []
     for ci, s in enumerate(range(0, n_reads, chunk)):
         n = min(chunk, n_reads - s)
-        jobs.append((seed, ci, n, read_len, n_genomes, glen, sigma, err, bool(bin_prefix) and s < bin_reads))
+        jobs.append((seed, first_read // chunk + ci, n, read_len, n_genomes, glen, sigma, err, bool(bin_prefix) and s < bin_reads))
     total = n_reads * read_len
     seq = np.zeros(total // 16 + 1, dtype=np.uint32)
     binf = open(bin_prefix + ".bin", "wb") if bin_prefix else None
