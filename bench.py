@@ -12,6 +12,7 @@ Workload at N GPUs: 20M x N reads of 150 bp (weak scaling; N=1 is BASELINE.json 
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -42,11 +43,20 @@ def parse():
     ap.add_argument("--sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--genomes-per-gpu", type=int, default=64)
+    ap.add_argument("--phases", action="store_true", help="diagnostic: per-phase host wall times of every rank on stderr (adds syncs)")
     ap.add_argument("--root-upload", action="store_true",
                     help="N>1: rank 0 uploads all reads and broadcasts them (default: every rank uploads its slice, NCCL all-gather)")
     ap.add_argument("--replicated-scan", action="store_true",
                     help="N>1: every shard scans ALL reads for its hash range (no item all-to-all); default is the scan-sharded stage 1")
     return ap.parse_args()
+
+
+def n_genomes(a, n_gpus):
+    """Weak scaling keeps the per-GPU work fixed: the community grows with the read set (64 genomes per 20M reads, the
+    density of BASELINE.json configs[1]), so coverage and the SdBG edges per read stay those of the 1-GPU workload.  With a
+    fixed community the edge count saturates as reads are added and edges/s would fall for reasons unrelated to the code."""
+    return a.genomes_per_gpu * n_gpus
 
 
 def workload_name(a, n_gpus):
@@ -66,7 +76,7 @@ def write_sample(a, work):
     from megagta_b200 import synth
     n = auto_sample(a)
     prefix = os.path.join(work, "sample")
-    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n)
+    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n, n_genomes=n_genomes(a, a.gpus))
     return prefix, n
 
 
@@ -108,7 +118,7 @@ def run_reference_arm(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(a, a.gpus), "sample": sample, "edges_per_step": edges},
+            "config": {"workload": workload_name(a, a.gpus), "genomes": n_genomes(a, a.gpus), "sample": sample, "edges_per_step": edges},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -117,45 +127,49 @@ def run_reference_arm(a):
 
 # ------------------------------------------------------------------------------------------------ our arm
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons of one GPU during the timed region.  NVML in-process (pynvml): spawning nvidia-smi
-    ten times a second measurably slows a step that synchronises with the host often (2-GPU step 246 -> 304 ms);
-    nvidia-smi remains the fallback when the binding is missing."""
+    """SM clock + throttle reasons of the job's GPUs during the timed region, sampled by rank 0 only, 4 times a second,
+    through NVML in-process (pynvml).  Measured: one nvidia-smi spawn per rank every 100 ms slowed the 2-GPU step from
+    246 to 304 ms, and even in-process NVML at 20 Hz on every rank cost the 4-GPU step 15 % (the queries serialise with
+    the other processes' driver calls).  nvidia-smi (2 Hz) remains the fallback when the binding is missing."""
     REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
 
-    def __init__(self, dev):
+    def __init__(self, devs):
         super().__init__(daemon=True)
-        self.dev, self.stop_flag, self.rows, self.max_mhz, self.source = dev, False, [], None, "nvidia-smi"
-        self.nvml = self.handle = None
+        self.devs, self.stop_flag, self.rows, self.max_mhz, self.source = list(devs), False, [], None, "nvidia-smi"
+        self.nvml, self.handles = None, []
         try:
             import pynvml
             import torch
             pynvml.nvmlInit()
-            try:
-                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)).encode())
-            except Exception:
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(dev)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            for d in self.devs:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(d).uuid)).encode())
+                except Exception:
+                    h = pynvml.nvmlDeviceGetHandleByIndex(d)
+                self.handles.append(h)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handles[0], pynvml.NVML_CLOCK_SM))
             self.nvml, self.source = pynvml, "nvml"
         except Exception:
-            self.nvml = self.handle = None
+            self.nvml, self.handles = None, []
 
     def sample_nvml(self):
         n = self.nvml
-        sm = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-        try:
-            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-        except Exception:
-            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-        self.rows.append((sm, mask))
+        for h in self.handles:
+            sm = int(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.rows.append((sm, mask))
 
     def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                           capture_output=True, text=True, timeout=5).stdout.strip()
-        if o:
-            f = [x.strip() for x in o.split(",")]
-            if f[0].isdigit():
+        o = subprocess.run(["nvidia-smi", "-i", ",".join(str(d) for d in self.devs), "--query-gpu=" + q,
+                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        for line in o.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6 and f[0].isdigit():
                 if f[1].isdigit():
                     self.max_mhz = int(f[1])
                 mask = sum(bit for (bit, _), v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active"))
@@ -170,15 +184,15 @@ class ClockSampler(threading.Thread):
                     self.sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05 if self.nvml else 0.5)
+            time.sleep(0.25 if self.nvml else 0.5)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": self.source}
         sm = sorted(r[0] for r in self.rows)
         reasons = [name for bit, name in self.REASONS if any(r[1] & bit for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows),
-                "source": self.source}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.rows), "gpus_sampled": len(self.devs), "source": self.source}
 
 
 class DevBuf:
@@ -218,14 +232,14 @@ def main():
     assert not sharded_upload or (a.reads_per_gpu * L) % 16 == 0 and a.reads_per_gpu % 1_000_000 == 0
     t0 = time.time()
     if sharded_upload:
-        seq, start = synth.packed_metagenome(a.reads_per_gpu, L, seed=a.seed, first_read=rank * a.reads_per_gpu,
+        seq, start = synth.packed_metagenome(a.reads_per_gpu, L, seed=a.seed, first_read=rank * a.reads_per_gpu, n_genomes=n_genomes(a, world),
                                              bin_prefix=sample_prefix if rank == 0 else None, bin_reads=sample_n if rank == 0 else 0,
                                              procs=max(1, (os.cpu_count() or 8) // world))
         seq_pin = torch.from_numpy(seq[:per_words].view(np.int32)).pin_memory()
         start_pin = torch.from_numpy((start[:a.reads_per_gpu] + np.uint64(rank * a.reads_per_gpu * L)).view(np.int64)).pin_memory()
         del seq, start
     elif rank == 0:
-        seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix, bin_reads=sample_n)
+        seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix, bin_reads=sample_n, n_genomes=n_genomes(a, world))
         seq_pin = torch.from_numpy(seq).pin_memory()
         start_pin = torch.from_numpy(start.view(np.int64)).pin_memory()
         del seq, start
@@ -266,21 +280,35 @@ def main():
         if world > 1:
             shards.exchange_ctx(ctx, rank, world, dist, dev)
 
+    phases = {}
+
+    def mark(name, t0):
+        if not a.phases:
+            return t0
+        torch.cuda.synchronize()
+        phases.setdefault(name, []).append(round((time.time() - t0) * 1000, 1))
+        return time.time()
+
     def step(e2e):
         """-> (edges of this shard, h2d bytes, d2h bytes)"""
+        t = time.time()
         h2d = load_reads() if e2e else 0
+        t = mark("load", t)
         d2h = 0
         if a.m > 1:
             if world > 1 and not a.replicated_scan:
                 shards.stage1_scan_sharded(ctx, n_reads, rank, world, dist, dev)
             else:
                 ctx.stage1()
+            t = mark("stage1", t)
             exchange_edges()
+            t = mark("edge_exchange", t)
         if e2e:
             nbytes, meta, totals = ctx.stage2(collect="count")
             d2h = nbytes + meta[slice(*ctx.shard_range())].nbytes
         else:
             ctx.stage2(collect=False)
+        mark("stage2", t)
         return ctx.stats(2)["n_edges"], h2d, d2h
 
     def timed(fn, reps):
@@ -289,9 +317,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()                                 # a collector pause on one rank stalls every rank at the next collective
         e0.record(stream)
         outs = [fn() for _ in range(reps)]
         e1.record(stream)
+        gc.enable()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -304,14 +335,16 @@ def main():
         load_reads()
         for _ in range(a.warmup):
             step(False)
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler = ClockSampler(range(world)) if rank == 0 else None     # rank 0 watches all GPUs of the job (one node)
+        if sampler:
+            sampler.start()
         ms_dev, outs = timed(lambda: step(False), a.steps)
         st1, st2 = ctx.stats(1), ctx.stats(2)
         step(True)      # untimed: the first end-to-end call allocates the library's pinned output staging (cudaHostAlloc)
         ms_e2e, outs_e2e = timed(lambda: step(True), a.steps)
-        sampler.stop_flag = True
-        sampler.join()
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join()
 
     def total(x):
         t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
@@ -326,6 +359,8 @@ def main():
             ref_s2_items = int(ctx.histogram(2).sum())
         except Exception:
             ref_s2_items = 0
+    if a.phases:
+        sys.stderr.write("rank %d phases(ms) %s\n" % (rank, json.dumps(phases)))
     edges = total(outs[-1][0])
     h2d = total(outs_e2e[-1][1])
     d2h = total(outs_e2e[-1][2])
@@ -385,6 +420,7 @@ def main():
                 "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
                 "config": {"workload": workload_name(a, n_gpus), "reads": n_reads, "read_len": L, "k": a.k, "min_count": a.m,
+                           "genomes": n_genomes(a, n_gpus),
                            "edges_per_step": edges, "s1_items": total_items(st1, world, dist, dev, torch),
                            "s2_items": total_items(st2, world, dist, dev, torch),
                            "l2": "inputs larger than L2 (item arrays are GBs per step); no explicit flush",

@@ -150,6 +150,10 @@ int mgta_edge_hist_device_buffer(mgta_ctx *ctx, void **dev, uint64_t *n_bytes);
  *      counts the received items exactly like mgta_stage1, leaving this shard's solid-edge rows for the edge exchange
  *      below.  edge_counting (may be NULL) is this shard's share: sum it over the shards.
  * Replaces, like mgta_stage1, cx1.run() with the s1 callbacks (build_graph.cpp:100-113). */
+/* Slab size for the equal partition of the reads (shard d scans reads [n_reads*d/world, n_reads*(d+1)/world)): the
+ * largest slice's edge offsets / world + 2 %.  Every shard holds all start_idx, so every shard computes the same
+ * value and no agreement round is needed.  Cached until the reads change. */
+int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items);
 int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t read_end, uint64_t slab_items, uint64_t *needed);
 int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev, uint64_t *slab_bytes,
                                  uint64_t *send_counts /* [world] */);

@@ -39,7 +39,7 @@ SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_
 EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_alloc_reads",
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
-           "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
+           "mgta_stage1_slab_items", "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
            "mgta_get_mercy_candidates", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
            "mgta_edge_hist_device_buffer", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version"]
@@ -68,6 +68,7 @@ def load():
         lib.mgta_stage1_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage2_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage1.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_stage1_slab_items.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_stage1_scan.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_stage1_exchange_buffers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
@@ -157,6 +158,12 @@ class Context:
         ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
         self._check(self.lib.mgta_stage1(self.h, _p(ec)), "mgta_stage1")
         return ec
+
+    def stage1_slab_items(self):
+        """slab size for the equal partition of the reads over the shards; identical on every shard (no collective)"""
+        n = ctypes.c_uint64()
+        self._check(self.lib.mgta_stage1_slab_items(self.h, ctypes.byref(n)), "mgta_stage1_slab_items")
+        return n.value
 
     def stage1_scan(self, read_begin, read_end, slab_items=0):
         """scan-sharded stage 1, step 1: items of reads [read_begin, read_end) binned by owner shard into send slabs of

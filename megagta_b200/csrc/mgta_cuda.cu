@@ -100,6 +100,7 @@ struct mgta_ctx {
     uint64_t n_positions = 0;              // edge offsets over all reads
     bool n_positions_valid = false;
     ExchangeState xch;
+    uint64_t slab_suggest = 0;             // cached mgta_stage1_slab_items() (0 = not computed for the current reads)
 };
 
 #define CK(call)                                                                                         \
@@ -317,6 +318,7 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     ctx->stage1_done = false;
     ctx->n_positions_valid = false;
     ctx->xch.valid = false;
+    ctx->slab_suggest = 0;
     return MGTA_OK;
 }
 }  // namespace
@@ -1388,6 +1390,28 @@ extern "C" int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t rea
     ctx->stage1_done = false;
     if ((rc = exchange_scan(ctx, read_begin, read_end, slab_items, needed, st))) return rc;
     return stage_end(ctx, st, tm);
+}
+
+extern "C" int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items) {
+    if (!ctx || !slab_items) return MGTA_ERR_ARG;
+    if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
+    const int world = ctx->opt.world;
+    if (world > MAX_OWNERS) FAIL(MGTA_ERR_ARG, "at most %d shards", (int)MAX_OWNERS);
+    if (!ctx->slab_suggest) {
+        CK(cudaSetDevice(ctx->opt.device));
+        unsigned long long *d_out = ctx->d_xs;                       // (MAX_OWNERS + 1) * 24 bytes: room for `world` counters
+        CK(cudaMemsetAsync(d_out, 0, (size_t)world * 8, ctx->stream));
+        k_count_positions_parts<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_reads, ctx->opt.kmer_k,
+                                                                                              (unsigned)world, d_out);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_pin, d_out, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint64_t mx = 0;
+        for (int d = 0; d < world; ++d) mx = std::max<uint64_t>(mx, ctx->h_pin[d]);
+        ctx->slab_suggest = ((uint64_t)((double)mx / world * 1.02) + 4096 + 31) & ~(uint64_t)31;
+    }
+    *slab_items = ctx->slab_suggest;
+    return MGTA_OK;
 }
 
 extern "C" int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev, uint64_t *slab_bytes,

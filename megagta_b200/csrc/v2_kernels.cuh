@@ -780,4 +780,28 @@ __global__ void k_count_positions(const uint64_t *__restrict__ start, uint64_t r
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 
+
+// edge offsets per equal slice of the reads: slice d = reads [n_reads * d / parts, n_reads * (d + 1) / parts)
+__global__ void k_count_positions_parts(const uint64_t *__restrict__ start, uint64_t n_reads, int k, unsigned parts, unsigned long long *out) {
+    const uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = r0 < n_reads;
+    const uint64_t r = valid ? r0 : n_reads - 1;
+    unsigned long long v = 0;
+    if (valid) {
+        const int64_t L = (int64_t)(start[r + 1] - start[r]);
+        if (L >= k + 1) v = (unsigned long long)(L - k);
+    }
+    unsigned d = (unsigned)(((unsigned __int128)r * parts) / n_reads);       // the d with n_reads*d/parts <= r < n_reads*(d+1)/parts
+    while (d + 1 < parts && (uint64_t)(((unsigned __int128)n_reads * (d + 1)) / parts) <= r) ++d;
+    while (d > 0 && (uint64_t)(((unsigned __int128)n_reads * d) / parts) > r) --d;
+    int same = 0;
+    __match_all_sync(0xFFFFFFFFu, d, &same);
+    if (same) {                                                              // the usual case: one slice per warp
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + d, v);
+    } else if (v) {
+        atomicAdd(out + d, v);
+    }
+}
+
 }  // namespace mgta

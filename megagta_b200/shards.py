@@ -58,32 +58,40 @@ def agree_max(value, dist, device):
     return int(t.item())
 
 
-def exchange_items(rank, world, dist, device, send, recv, send_counts):
+def share_counts(rank, world, dist, device, send_counts, need):
+    """One all-gather tells every shard what every shard sends to whom, and the largest slab any shard needs.
+    -> (items this shard receives from each shard, max need)"""
+    mine = torch.as_tensor([int(x) for x in send_counts] + [int(need)], dtype=torch.int64).to(device)
+    table = torch.empty(world * (world + 1), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(table, mine)
+    t = table.view(world, world + 1).cpu()
+    return [int(t[s, rank]) for s in range(world)], int(t[:, world].max())
+
+
+def exchange_items(rank, world, dist, device, send, recv):
     """All-to-all of the stage-1 items between the scan and the count step.  send / recv: int32 tensors of `world`
-    equal slabs (slab d of `send` goes to shard d, slab s of `recv` comes from shard s); send_counts: items per send
-    slab.  Returns the items received from every shard (list of world ints)."""
-    sc = torch.as_tensor([int(x) for x in send_counts], dtype=torch.int64).to(device)
-    rc = torch.empty_like(sc)
-    dist.all_to_all_single(rc, sc)
+    equal slabs (slab d of `send` goes to shard d, slab s of `recv` comes from shard s)."""
     dist.all_to_all_single(recv, send)
-    return [int(x) for x in rc.tolist()]
 
 
 def stage1_scan_sharded(ctx, n_reads, rank, world, dist, device):
     """Scan-sharded stage 1 over a cabi.Context: scan my slice of the reads, all-to-all the items over NCCL, count.
     Returns this shard's share of edge_counting (numpy int64[65536])."""
     lo, hi = read_range(n_reads, rank, world)
-    slab = agree_max(ctx.stage1_scan(lo, hi, 0), dist, device)
-    need = agree_max(ctx.stage1_scan(lo, hi, slab), dist, device)
-    if need > slab:                                   # a send slab overflowed somewhere (skewed input): one rescan that fits
-        slab = need
-        need = agree_max(ctx.stage1_scan(lo, hi, slab), dist, device)
-        if need > slab:
-            raise RuntimeError("stage-1 send slabs overflow after the rescan")
-    sp, rp, slab_bytes, counts = ctx.stage1_exchange_buffers()
+    slab = ctx.stage1_slab_items()                    # the same on every shard: computed from start_idx, no collective
+    for attempt in range(2):
+        need = ctx.stage1_scan(lo, hi, slab)
+        counts = ctx.stage1_exchange_buffers()[3] if need <= slab else [0] * world
+        got, need = share_counts(rank, world, dist, device, counts, need)
+        if need <= slab:
+            break
+        slab = need                                   # a send slab overflowed somewhere (skewed input): one rescan that fits
+    else:
+        raise RuntimeError("stage-1 send slabs overflow after the rescan")
+    sp, rp, slab_bytes, _ = ctx.stage1_exchange_buffers()
     send = torch.as_tensor(DevBuf(sp, world * slab_bytes), device=device)
     recv = torch.as_tensor(DevBuf(rp, world * slab_bytes), device=device)
-    got = exchange_items(rank, world, dist, device, send, recv, counts)
+    exchange_items(rank, world, dist, device, send, recv)
     return ctx.stage1_count(got)
 
 

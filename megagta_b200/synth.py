@@ -77,7 +77,18 @@ def write_variable_reads(prefix, reads):
 # Parallel in-memory generator for the bench workloads (same model as metagenome_reads, one RNG stream
 # per 1M-read chunk so chunks can be produced by worker processes).
 
+_GENOME_CACHE = {}
+
+
 def _genomes(seed, n_genomes, glen, sigma):
+    key = (seed, n_genomes, tuple(glen), sigma)
+    if key not in _GENOME_CACHE:          # filled by the parent before the worker pool forks: workers inherit it
+        _GENOME_CACHE.clear()
+        _GENOME_CACHE[key] = _make_genomes(seed, n_genomes, glen, sigma)
+    return _GENOME_CACHE[key]
+
+
+def _make_genomes(seed, n_genomes, glen, sigma):
     rng = np.random.default_rng(seed)
     gl = rng.integers(glen[0], glen[1], size=n_genomes)
     G = [rng.integers(0, 4, size=int(n), dtype=np.uint8) for n in gl]
@@ -140,6 +151,7 @@ def packed_metagenome(n_reads, read_len, seed=20261017, n_genomes=64, glen=(200_
     seq = np.zeros(total // 16 + 1, dtype=np.uint32)
     binf = open(bin_prefix + ".bin", "wb") if bin_prefix else None
     written = 0
+    _genomes(seed, n_genomes, glen, sigma)
     with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
         for ci, (words, rec) in enumerate(pool.imap(_chunk_packed, jobs)):
             w0 = ci * chunk * read_len // 16

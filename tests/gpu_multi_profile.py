@@ -34,14 +34,15 @@ with torch.cuda.stream(stream):
         dist.broadcast(torch.as_tensor(shards.DevBuf(tp, tb), device=dev), 0)
         t = tick("bcast", t)
         lo, hi = shards.read_range(n_reads, rank, world)
-        slab = shards.agree_max(ctx.stage1_scan(lo, hi, 0), dist, dev)
+        slab = ctx.stage1_slab_items()
         t = tick("scan_size", t)
-        need = shards.agree_max(ctx.stage1_scan(lo, hi, slab), dist, dev)
+        need = ctx.stage1_scan(lo, hi, slab)
         t = tick("scan", t)
         sp, rp, slab_bytes, counts = ctx.stage1_exchange_buffers()
+        got, need = shards.share_counts(rank, world, dist, dev, counts, need)
         send = torch.as_tensor(shards.DevBuf(sp, world * slab_bytes), device=dev)
         recv = torch.as_tensor(shards.DevBuf(rp, world * slab_bytes), device=dev)
-        got = shards.exchange_items(rank, world, dist, dev, send, recv, counts)
+        shards.exchange_items(rank, world, dist, dev, send, recv)
         t = tick("a2a", t)
         ctx.stage1_count(got)
         t = tick("count", t)

@@ -211,7 +211,10 @@ def test_gpu_scan_sharded_stage1_exchange(read_lib, ds, k, m, cap):
             for c in ctxs:
                 c.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
             ranges = [shards.read_range(n_reads, r, world) for r in range(world)]
-            slab = 64 if cap else max(c.stage1_scan(lo, hi, 0) for c, (lo, hi) in zip(ctxs, ranges))
+            sizes = {c.stage1_slab_items() for c in ctxs}
+            assert len(sizes) == 1                       # every shard derives the same slab size from start_idx: no agreement round
+            assert max(c.stage1_scan(lo, hi, 0) for c, (lo, hi) in zip(ctxs, ranges)) <= min(sizes)
+            slab = 64 if cap else min(sizes)
             need = max(c.stage1_scan(lo, hi, slab) for c, (lo, hi) in zip(ctxs, ranges))
             if cap:
                 assert need > slab                       # the 64-item slabs must overflow and report the size that fits
