@@ -39,12 +39,22 @@ __device__ __forceinline__ int key_cmp(const uint32_t *keys, unsigned capi, unsi
 // take the LSD path below.
 
 template <int W>
-__device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *hist, unsigned capi, unsigned n, int kb, int D,
-                                                 unsigned *s_big, unsigned big_bin) {
+__device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, unsigned capi, unsigned n, int kb, int D,
+                                                 unsigned *s_big, unsigned big_bin, int k) {
+    // bin counters: u16 pairs packed in the (otherwise idle) per-warp LSD counter array -- 32-bit shared atomics on the
+    // half that belongs to the bin return the arrival rank; <= 4096 items per window, so a half never carries over.
+    // qk[i]: the 32 key bits that follow the bin bits.  When what is left of `S a` fits in 28 bits (k = 31: always) the
+    // low 4 bits hold the flag nibble ((a != $) << 3 | b) and qk alone orders a bin: the comparison rank reads ONE word
+    // per pair.  Longer keys compare the remaining key words only when qk ties.
+    uint32_t *hist = reinterpret_cast<uint32_t *>(S.whist);       // [NB / 2] packed (low half = even bin)
     const unsigned NB = 1u << D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (unsigned i = tid; i < NB; i += CHUNK_THREADS) hist[i] = 0;
+    for (unsigned i = tid; i < NB / 2; i += CHUNK_THREADS) hist[i] = 0;
     if (tid == 0) *s_big = 0;
     __syncthreads();
+    const int q_off = kb + D;                                     // first key bit below the bin bits
+    const int left = 2 * (k - 1) + 2 - q_off;                     // bits of `S a` below the bin bits
+    const bool exact = left <= 28;
+    const int qw = q_off >> 5, qs = q_off & 31;
     unsigned short dg[8], rk[8];
     bool big = false;
 #pragma unroll
@@ -52,22 +62,29 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *hist, u
         const unsigned i = tid + r * CHUNK_THREADS;
         if (i < n) {
             const unsigned d = (S.keys[i] << kb) >> (32 - D);
-            const unsigned a = atomicAdd(&hist[d], 1u);
+            const unsigned sh = (d & 1u) * 16u;
+            const unsigned a = (atomicAdd(&hist[d >> 1], 1u << sh) >> sh) & 0xFFFFu;
             dg[r] = (unsigned short)d; rk[r] = (unsigned short)a;
             big = big || a >= big_bin;
+            const uint32_t k0 = qw < W ? S.keys[qw * capi + i] : 0u;
+            const uint32_t k1 = qw + 1 < W ? S.keys[(qw + 1) * capi + i] : 0u;
+            uint32_t q = __funnelshift_l(k1, k0, qs);             // 32 key bits from bit q_off on
+            if (exact) q = left > 0 ? (((q >> (32 - left)) << 4) | (S.keys[(W - 1) * capi + i] & 15u)) : (S.keys[(W - 1) * capi + i] & 15u);
+            qk[i] = q;
         }
     }
     if (big) *s_big = 1;
     __syncthreads();
     if (*s_big) return false;
-    // exclusive scan of the bin counters: `per` consecutive counters per thread
+    // exclusive scan of the bin counters: `per` consecutive bins per thread (per even, or NB < CHUNK_THREADS * 2)
     {
-        const unsigned per = NB >= CHUNK_THREADS ? NB / CHUNK_THREADS : 1u;       // <= 8
+        const unsigned per = NB >= 2 * CHUNK_THREADS ? NB / CHUNK_THREADS : 2u;   // 2 .. 8 bins = 1 .. 4 packed words
         unsigned c[8], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned b = tid * per + j;
-            c[j] = ((unsigned)j < per && b < NB) ? hist[b] : 0u;
+        for (int j = 0; j < 4; ++j) {
+            const unsigned b = tid * per + 2 * j;
+            const uint32_t v = ((unsigned)(2 * j) < per && b < NB) ? hist[b >> 1] : 0u;
+            c[2 * j] = v & 0xFFFFu; c[2 * j + 1] = v >> 16;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const unsigned t = c[j]; c[j] = sum; sum += t; }
@@ -88,36 +105,44 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *hist, u
         const unsigned add = warp ? __shfl_sync(0xFFFFFFFFu, ws, warp - 1) : 0u;
         const unsigned excl = x - sum + add;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned b = tid * per + j;
-            if ((unsigned)j < per && b < NB) hist[b] = excl + c[j];
+        for (int j = 0; j < 4; ++j) {
+            const unsigned b = tid * per + 2 * j;
+            if ((unsigned)(2 * j) < per && b < NB) hist[b >> 1] = (excl + c[2 * j]) | ((excl + c[2 * j + 1]) << 16);   // starts <= 4096 fit 16 bits
         }
     }
     __syncthreads();
+    const uint16_t *hs = reinterpret_cast<const uint16_t *>(hist);                 // bin start by bin index (little endian halves)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const unsigned i = tid + r * CHUNK_THREADS;
-        if (i < n) S.pb[hist[dg[r]] + rk[r]] = (uint16_t)i;
+        if (i < n) S.pb[(unsigned)hs[dg[r]] + rk[r]] = (uint16_t)i;
     }
     __syncthreads();
+    const int tw = (q_off + 32) >> 5;                             // first key word not fully covered by qk
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const unsigned i = tid + r * CHUNK_THREADS;
         if (i < n) {
             const unsigned d = dg[r];
-            const unsigned s = hist[d], e = d + 1 < NB ? hist[d + 1] : n;
+            const unsigned s = hs[d], e = d + 1 < NB ? (unsigned)hs[d + 1] : n;
             unsigned pos = s;
             if (e - s > 1) {
-                uint32_t mine[W];
-#pragma unroll
-                for (int w = 0; w < W; ++w) mine[w] = S.keys[w * capi + i];
+                const uint32_t mq = qk[i];
                 for (unsigned j = s; j < e; ++j) {
                     const unsigned o = S.pb[j];
-                    bool less = o < i;                                             // equal keys: by item index
+                    const uint32_t oq = qk[o];
+                    bool less = oq < mq;
+                    if (oq == mq) {
+                        less = o < i;                                              // equal keys: by item index
+                        if (!exact) {
 #pragma unroll
-                    for (int w = W - 1; w >= 0; --w) {
-                        const uint32_t x = S.keys[w * capi + o];
-                        less = x < mine[w] || (x == mine[w] && less);
+                            for (int w = W - 1; w >= 0; --w) {
+                                if (w >= tw) {
+                                    const uint32_t x = S.keys[w * capi + o], y = S.keys[w * capi + i];
+                                    less = x < y || (x == y && less);
+                                }
+                            }
+                        }
                     }
                     pos += (o != i && less) ? 1u : 0u;
                 }
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
         //      then the S bits [kb, 2(k-1)) from the least significant byte up.  One __match_any_sync per item and pass;
         //      digit, warp-local rank and item stay in registers between the counting and the scatter half.
         bool sorted = n <= 1;
-        if (!sorted && P.bin_bits > 0) sorted = bucket_rank_sort<W>(S, fld, capi, n, kb, P.bin_bits, &s_big, P.big_bin);
+        if (!sorted && P.bin_bits > 0) sorted = bucket_rank_sort<W>(S, fld, capi, n, kb, P.bin_bits, &s_big, P.big_bin, P.k);
         if (!sorted) {
             if (tid == 0 && P.n_lsd) atomicAdd(P.n_lsd, 1u);
             const unsigned slice = (((n + CHUNK_WARPS - 1) / CHUNK_WARPS) + 31) & ~31u;
