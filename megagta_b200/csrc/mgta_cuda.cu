@@ -96,7 +96,8 @@ struct mgta_ctx {
     bool solid_valid = false;              // d_solid holds the is_solid vector of the last stage 1 (derived on demand)
     bool stage1_done = false;
     uint32_t *d_hist_s2 = nullptr;
-    int PB = 20;                           // prefix bits of a stage-2 tile: min(20, 2(k-1)), >= 16
+    int PB = 20;                           // prefix bits of a stage-2 tile: min(20 + log2(world), 24, 2(k-1)), >= 16
+    uint32_t *h_hist2 = nullptr;           // pinned copy of d_hist_s2
     uint64_t n_positions = 0;              // edge offsets over all reads
     bool n_positions_valid = false;
     ExchangeState xch;
@@ -270,8 +271,17 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_totals, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ec, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ctr, CTR_COUNT * 4)) != cudaSuccess) return fail("cudaMalloc", e);
-    ctx->PB = std::min(20, 2 * (opts->kmer_k - 1));
+    // stage-2 prefix tiles: 2^20 for one GPU; the item count grows with the shards (weak scaling), so each doubling of the
+    // world adds a prefix bit and the tiles keep their size (measured at 8 GPUs with 2^20 tiles: every tile overflows
+    // the on-chip window, MSD levels run for all of them and the sort slows from 67 to 96 ms).
+    {
+        int wb = 0;
+        while ((1 << wb) < opts->world) ++wb;
+        ctx->PB = std::min(std::min(20 + wb, 24), 2 * (opts->kmer_k - 1));
+        if (const char *e2 = getenv("MGTA_S2_PB")) ctx->PB = std::max(16, std::min(std::min(atoi(e2), 24), 2 * (opts->kmer_k - 1)));   // test hook
+    }
     if ((e = cudaMalloc(&ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaHostAlloc(&ctx->h_hist2, ((size_t)1 << ctx->PB) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaMalloc(&ctx->d_xs, (size_t)(MAX_OWNERS + 1) * 24)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     *out = ctx;
@@ -286,7 +296,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
     cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs);
-    cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out);
+    cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_hist2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1052,7 +1062,10 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     const int W = key_words_s2(k), IW = W + 1;
     const bool plus = W > WE;
     const int PB = ctx->PB;
-    const unsigned lb1 = (unsigned)PB / 2, lb2 = (unsigned)PB - lb1, B1 = 1u << lb1, NT = 1u << PB;
+    // two partition levels: level-2 fan-out <= 1024 tiles per level-1 bin; a batch handles <= MAX_BINS level-1 bins,
+    // numbered relative to its first one (g1_lo), so any number of global level-1 bins works
+    const unsigned lb1 = (unsigned)std::max(PB - 10, PB / 2), lb2 = (unsigned)PB - lb1, NT = 1u << PB;
+    const unsigned B1 = std::min(1u << lb1, (unsigned)MAX_BINS), NTB = B1 << lb2;      // per-batch maxima
     const unsigned tiles_per_bucket = 1u << (PB - 16);
     int rc;
     st->key_words = W; st->item_words = IW;
@@ -1062,8 +1075,8 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     st->sort_cap = (int)pl.CAPI;
 
     // tile histogram -> host: lv1 bucket sizes, shard range, batches
-    std::vector<uint32_t> h2(NT);
-    CK(cudaMemcpyAsync(h2.data(), ctx->d_hist_s2, (size_t)NT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const uint32_t *h2 = ctx->h_hist2;
+    CK(cudaMemcpyAsync(ctx->h_hist2, ctx->d_hist_s2, (size_t)NT * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->hist.assign(NUM_BUCKETS, 0);
     uint64_t total = 0;
@@ -1091,7 +1104,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         L.win = c.take(n_win * 4); L.state = c.take((2 * n_win + 4) * 8);
         L.list0 = c.take((size_t)pl.list_cap * sizeof(Seg)); L.list1 = c.take((size_t)pl.list_cap * sizeof(Seg));
         L.giants = c.take((size_t)pl.giants_cap * sizeof(Giant));
-        L.loc = c.take((size_t)NT * 4); L.off2 = c.take(((size_t)NT + 1) * 8); L.cur2 = c.take((size_t)NT * 8);
+        L.loc = c.take((size_t)NTB * 4); L.off2 = c.take(((size_t)NTB + 1) * 8); L.cur2 = c.take((size_t)NTB * 8);
         L.tot = c.take((B1 + 1) * 8); L.base = c.take((B1 + 1) * 8); L.in_start = c.take((B1 + 1) * 8);
         L.chunk_pref = c.take((B1 + 1) * 4); L.cur1 = c.take((B1 + 1) * 8);
         L.out = c.take(pl.out_cap);
@@ -1133,7 +1146,9 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     while (b0 < ctx->shard_hi) {
         int b1 = b0;
         uint64_t n_items = 0;
-        while (b1 < ctx->shard_hi && n_items + (uint64_t)ctx->hist[b1] <= pl.cap) { n_items += (uint64_t)ctx->hist[b1]; ++b1; }
+        const unsigned g1_lo = ((unsigned)b0 * tiles_per_bucket) >> lb2;                    // first (global) level-1 bin of the batch
+        while (b1 < ctx->shard_hi && n_items + (uint64_t)ctx->hist[b1] <= pl.cap &&
+               ((((unsigned)b1 + 1) * tiles_per_bucket - 1) >> lb2) - g1_lo < (unsigned)MAX_BINS) { n_items += (uint64_t)ctx->hist[b1]; ++b1; }
         if (b1 == b0) FAIL(MGTA_ERR_MEM, "bucket %d (%lld items) exceeds the batch capacity %llu", b0, (long long)ctx->hist[b0], (unsigned long long)pl.cap);
         st->n_batches++;
         if (n_items == 0) {
@@ -1145,6 +1160,8 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
             continue;
         }
         const unsigned t_lo = (unsigned)b0 * tiles_per_bucket, t_hi = (unsigned)b1 * tiles_per_bucket;
+        const unsigned nb1 = ((t_hi - 1) >> lb2) - g1_lo + 1;                               // level-1 bins the batch touches (<= MAX_BINS)
+        const unsigned rt_lo = t_lo - (g1_lo << lb2), rt_hi = t_hi - (g1_lo << lb2);          // its tiles, batch relative
         const unsigned n_windows = (unsigned)((n_items + pl.C - 1) / pl.C);
         CK(cudaMemsetAsync(flags, 0, (n_items / 32 + 64) * 4, ctx->stream));
         CK(cudaMemsetAsync(win, 0, ((size_t)n_windows + 2) * 4, ctx->stream));
@@ -1153,7 +1170,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         // ---- exact offsets of the batch's tiles
         ScanParams SP;
         memset(&SP, 0, sizeof(SP));
-        SP.hist = ctx->d_hist_s2; SP.NT = NT; SP.lb2 = lb2; SP.t_lo = t_lo; SP.t_hi = t_hi;
+        SP.hist = ctx->d_hist_s2 + ((size_t)g1_lo << lb2); SP.NT = nb1 << lb2; SP.lb2 = lb2; SP.t_lo = rt_lo; SP.t_hi = rt_hi;
         SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
         SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
         SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
@@ -1170,7 +1187,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         memset(&IP, 0, sizeof(IP));
         IP.edges = ctx->edges_all_valid ? ctx->d_edges_all : ctx->d_edges;
         IP.n_edges = ctx->edges_all_valid ? ctx->n_edges_all : ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
-        IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = B1; IP.dst = bufA; IP.cap = pl.cap;
+        IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = nb1; IP.b1_lo = g1_lo; IP.dst = bufA; IP.cap = pl.cap;
         IP.err = ctx->d_ctr + CTR_ERR;
         if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
         if (launch_item_part(WE, plus, IP, (unsigned)((IP.n_edges + ITEM_EDGES - 1) / ITEM_EDGES), ctx->stream))
@@ -1182,10 +1199,10 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         memset(&XP, 0, sizeof(XP));
         XP.src = bufA; XP.dst = bufB; XP.cap_src = pl.cap; XP.cap_dst = pl.cap; XP.IW = IW; XP.WE = W; XP.mode = 1;
         XP.sh2 = 32 - PB; XP.lb2 = lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
-        XP.B1 = B1; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET2; XP.T = T; XP.err = ctx->d_ctr + CTR_ERR;
+        XP.B1 = nb1; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET2; XP.T = T; XP.err = ctx->d_ctr + CTR_ERR;
         if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
         if ((rc = launch_split(ctx, XP))) return rc;
-        k_flags_tiles<<<(t_hi - t_lo + 255) / 256, 256, 0, ctx->stream>>>(off2, t_lo, t_hi, flags);
+        k_flags_tiles<<<(rt_hi - rt_lo + 255) / 256, 256, 0, ctx->stream>>>(off2, rt_lo, rt_hi, flags);
         CK(cudaGetLastError());
         st->n_launches += 6;
         seg_host.clear();

@@ -706,8 +706,8 @@ struct ItemPartParams {
     unsigned long long n_edges;
     int k, sh1;                       // level-1 bin = key word 0 >> sh1
     unsigned bkt_lo, bkt_hi;          // lv1 buckets (top 16 key bits) of this batch
-    unsigned long long *cursor1;      // [B1] exact absolute starts
-    unsigned NB;
+    unsigned long long *cursor1;      // [NB] exact absolute starts of the batch's level-1 bins
+    unsigned NB, b1_lo;               // level-1 bins of the batch: global bins [b1_lo, b1_lo + NB)
     uint32_t *dst;
     uint64_t cap;
     unsigned *err;
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams
             const unsigned bkt = y[0] >> 16;
             if (bkt >= P.bkt_lo && bkt < P.bkt_hi) {
                 const int slot = el * 6 + j;
-                const unsigned b = y[0] >> P.sh1;
+                const unsigned b = (y[0] >> P.sh1) - P.b1_lo;
 #pragma unroll
                 for (int w = 0; w < W2; ++w) S.stage[w * SLOTS + slot] = y[w];
                 S.stage[W2 * SLOTS + slot] = mult;
