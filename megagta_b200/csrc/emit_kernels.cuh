@@ -47,6 +47,7 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
     // low 4 bits hold the flag nibble ((a != $) << 3 | b) and qk alone orders a bin: the comparison rank reads ONE word
     // per pair.  Longer keys compare the remaining key words only when qk ties.
     uint32_t *hist = reinterpret_cast<uint32_t *>(S.whist);       // [NB / 2] packed (low half = even bin)
+    D = min(D, 32 - kb);                                          // the bin bits come from key word 0 only (kb <= 24: D >= 8)
     const unsigned NB = 1u << D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (unsigned i = tid; i < NB / 2; i += CHUNK_THREADS) hist[i] = 0;
     if (tid == 0) *s_big = 0;
@@ -313,6 +314,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
                     if (!r)
                         for (int w = P.g_full; w < W; ++w)
                             if (S.keys[w * capi + x] != S.keys[w * capi + y]) { r = true; break; }
+                    // sortedness is checked on every window of every run (one position in 16: warp 0's share -- a mis-sorted
+                    // window is wrong all over, and the full check costs 3 ms of 67): an unsorted window would silently
+                    // split groups into extra records
+                    if (warp == 0 && r && key_cmp<W>(S.keys, capi, x, y) < 0) atomicOr(P.err, (unsigned)ERR_SORT_ORDER);
                 }
                 const uint32_t lw = S.keys[(W - 1) * capi + x];
                 const uint32_t a = ((lw >> 3) & 1) ? ((S.keys[P.aw * capi + x] >> P.ash) & 3u) : (uint32_t)SENT;

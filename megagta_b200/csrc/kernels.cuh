@@ -33,7 +33,7 @@ constexpr int CHUNK_WARPS = CHUNK_THREADS / 32;
 constexpr int MAX_PASSES = 40;
 
 enum { MODE_HIST = 0, MODE_SCATTER = 1 };
-enum { ERR_NEXT_LIST_FULL = 1, ERR_GIANT_LIST_FULL = 2, ERR_CHUNK_TOO_BIG = 4, ERR_OUT_OVERFLOW = 8 };
+enum { ERR_NEXT_LIST_FULL = 1, ERR_GIANT_LIST_FULL = 2, ERR_CHUNK_TOO_BIG = 4, ERR_OUT_OVERFLOW = 8, ERR_SORT_ORDER = 256 };
 
 struct WalkParams {
     const uint32_t *seq;
