@@ -8,6 +8,7 @@
 // parses options, loads and reverses the packed reads, and writes files.  There is no CPU fallback.
 //
 //   megagta_b200 buildgraph -k 31 -m 2 --host_mem 8e9 --read_lib_file X --output_prefix P [--num_cpu_threads T ...]
+#include <ctype.h>
 #include <errno.h>
 #include <getopt.h>
 #include <stdint.h>
@@ -173,6 +174,83 @@ Reads load_read_lib(const std::string &prefix, int threads) {
     return R;
 }
 
+// ---- --assist_seq (reference s1.cpp:104-134): a fast[aq] file (optionally gzip'ed) whose sequences are appended after the
+// short reads through SequencePackage::AppendReverseSeq -- reversed, un-trimmed, chars mapped by dna_map
+// (ACGTNacgtn -> 0123201232, sequence_package.h:67-69; anything else -> 0).  `<file>.info` holds `num_seq num_bases`.
+// Assist reads count in stage 1 but never get is_solid bits; all their edges are solid in stage 2 (s2.cpp:276,529).
+void append_assist(Reads &R, const std::string &file) {
+    long long n_seq_info = 0, n_bases_info = 0;
+    {
+        FILE *f = fopen((file + ".info").c_str(), "r");
+        if (!f) die("cannot open " + file + ".info: " + strerror(errno));
+        if (fscanf(f, "%lld%lld", &n_seq_info, &n_bases_info) != 2) die("bad " + file + ".info (expected: num_seq num_bases)");
+        fclose(f);
+    }
+    gzFile gz = gzopen(file.c_str(), "rb");
+    if (!gz) die("cannot open " + file);
+    gzbuffer(gz, 1 << 20);
+    unsigned char map[256];
+    memset(map, 0, sizeof(map));
+    { const char *a = "ACGTNacgtn", *b = "0123201232"; for (int i = 0; i < 10; ++i) map[(unsigned char)a[i]] = (unsigned char)(b[i] - '0'); }
+    // kseq-style record reader: '>' or '@' header; sequence lines up to the next header ('>' / '@') or '+' (then as many
+    // quality characters as bases are skipped)
+    std::vector<std::string> seqs;
+    std::string line, cur;
+    bool in_seq = false;
+    auto getline_gz = [&](std::string &out) {
+        out.clear();
+        char buf[1 << 16];
+        bool any = false;
+        while (gzgets(gz, buf, sizeof(buf))) {
+            any = true;
+            const size_t n = strlen(buf);
+            out.append(buf, n);
+            if (n && buf[n - 1] == '\n') break;
+        }
+        while (!out.empty() && (out.back() == '\n' || out.back() == '\r')) out.pop_back();
+        return any;
+    };
+    while (getline_gz(line)) {
+        if (line.empty()) continue;
+        if (line[0] == '>' || line[0] == '@') {
+            if (in_seq) seqs.push_back(cur);
+            cur.clear();
+            in_seq = true;
+        } else if (line[0] == '+' && in_seq) {
+            size_t q = 0;
+            while (q < cur.size() && getline_gz(line)) q += line.size();
+            seqs.push_back(cur);
+            cur.clear();
+            in_seq = false;
+        } else if (in_seq) {
+            for (char c : line) if (!isspace((unsigned char)c)) cur.push_back(c);
+        }
+    }
+    if (in_seq) seqs.push_back(cur);
+    gzclose(gz);
+    unsigned long long extra = 0;
+    for (auto &q : seqs) extra += q.size();
+    if ((long long)seqs.size() != n_seq_info || (long long)extra != n_bases_info)
+        fprintf(stderr, "[B200] warning: %s holds %zu sequences / %llu bases, its .info says %lld / %lld\n", file.c_str(), seqs.size(),
+                extra, n_seq_info, n_bases_info);
+    const uint64_t total = R.start.back() + extra;
+    const uint64_t new_words = total / 16 + 1;
+    uint32_t *ns = (uint32_t *)calloc(new_words + 4, 4);
+    if (!ns) die("out of host memory for the assist sequences");
+    memcpy(ns, R.seq, R.n_words * 4);
+    free(R.seq);
+    R.seq = ns; R.n_words = new_words;
+    uint64_t g = R.start.back();
+    for (auto &q : seqs) {
+        for (size_t i = q.size(); i-- > 0;) {                  // reversed, not complemented
+            ns[g >> 4] |= (uint32_t)map[(unsigned char)q[i]] << ((15 - (g & 15)) * 2);
+            ++g;
+        }
+        R.start.push_back(g);
+    }
+    R.n_reads += seqs.size();
+}
+
 // ---- SdbgWriter equivalent: one record file per shard (here one), sdbg_info in the reference's exact text format
 struct Writer {
     std::string prefix;
@@ -204,13 +282,18 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 int build_graph(int argc, char **argv) {
     const double t0 = now();
     Options opt = parse(argc, argv);
-    if (!opt.assist_seq_file.empty()) die("--assist_seq is not supported by the B200 driver yet (SURVEY 8f row 2)");
     if (opt.need_mercy) die("--need_mercy is not supported by the B200 driver yet (SURVEY 8f row 1)");
 
     Reads R = load_read_lib(opt.read_lib_file, opt.num_cpu_threads);
     fprintf(stderr, "[B200] %llu reads, %llu bases, max length %d, loaded in %.2f s\n", (unsigned long long)R.n_reads,
             (unsigned long long)R.start.back(), R.max_len, now() - t0);
     if (R.n_reads == 0) die("empty read library");
+    const uint64_t n_short = R.n_reads;                          // max_len stays that of the short reads (s1.cpp:119)
+    if (!opt.assist_seq_file.empty()) {
+        append_assist(R, opt.assist_seq_file);
+        fprintf(stderr, "[B200] %llu assist sequences, %llu bases in all\n", (unsigned long long)(R.n_reads - n_short),
+                (unsigned long long)R.start.back());
+    }
 
     mgta_opts mo;
     memset(&mo, 0, sizeof(mo));
@@ -222,7 +305,7 @@ int build_graph(int argc, char **argv) {
     auto ck = [&](int rc, const char *what) { if (rc != 0) die(std::string(what) + ": " + mgta_last_error(ctx)); };
 
     const double t1 = now();
-    ck(mgta_set_reads(ctx, R.seq, R.n_words, R.start.data(), R.n_reads, R.n_reads, R.max_len), "mgta_set_reads");
+    ck(mgta_set_reads(ctx, R.seq, R.n_words, R.start.data(), R.n_reads, n_short, R.max_len), "mgta_set_reads");
     if (opt.min_count > 1) {
         std::vector<int64_t> ec(MGTA_NUM_BUCKETS, 0);
         ck(mgta_stage1(ctx, ec.data()), "mgta_stage1");

@@ -77,6 +77,8 @@ def exchange_items(rank, world, dist, device, send, recv):
 def stage1_scan_sharded(ctx, n_reads, rank, world, dist, device):
     """Scan-sharded stage 1 over a cabi.Context: scan my slice of the reads, all-to-all the items over NCCL, count.
     Returns this shard's share of edge_counting (numpy int64[65536])."""
+    if getattr(ctx, "n_short", n_reads) < n_reads:    # assist reads: the replicated scan tells their occurrences apart
+        return ctx.stage1()
     lo, hi = read_range(n_reads, rank, world)
     slab = ctx.stage1_slab_items()                    # the same on every shard: computed from start_idx, no collective
     for attempt in range(2):

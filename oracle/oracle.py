@@ -119,6 +119,45 @@ def load_read_lib(prefix):
     return dict(seq=seq, start=start, n_reads=len(lens), max_len=int(lens.max()) if len(lens) else 0)
 
 
+def with_assist(rd, fasta):
+    """rd + the sequences of a FASTA file appended as assist reads (reference s1.cpp:104-134 ->
+    SequencePackage::AppendReverseSeq: reversed, un-trimmed, dna_map ACGTNacgtn -> 0123201232, sequence_package.h:67-69).
+    -> (new read dict, n_short).  max_len stays that of the short reads (s1.cpp:119)."""
+    code = np.zeros(256, dtype=np.uint8)
+    for c, v in zip("ACGTNacgtn", "0123201232"):
+        code[ord(c)] = int(v)
+    seqs, cur = [], None
+    for line in open(fasta):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            if cur is not None:
+                seqs.append("".join(cur))
+            cur = []
+        elif cur is not None:
+            cur.append(line)
+    if cur is not None:
+        seqs.append("".join(cur))
+    lens, offs, raw = None, None, None
+    n0 = rd["n_reads"]
+    old_bases = unpack_stream(rd["seq"], int(rd["start"][-1]))
+    extra = [code[np.frombuffer(q.encode(), dtype=np.uint8)][::-1] for q in seqs]
+    bases = np.concatenate([old_bases] + extra) if extra else old_bases
+    start = np.concatenate([rd["start"].astype(np.uint64),
+                            (int(rd["start"][-1]) + np.cumsum([len(e) for e in extra])).astype(np.uint64)])
+    pad = (-len(bases)) % 16
+    b = np.concatenate([bases, np.zeros(pad + 16, dtype=np.uint8)]).reshape(-1, 16).astype(np.uint32)
+    sh = (2 * (15 - np.arange(16))).astype(np.uint32)
+    seq = (b << sh).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    return dict(seq=seq, start=start, n_reads=n0 + len(seqs), max_len=rd["max_len"]), n0
+
+
+def unpack_stream(seq, n_bases):
+    """u32 words (16 bases each, MSB first) -> uint8 bases[n_bases]"""
+    w = np.asarray(seq, dtype=np.uint32)[: (n_bases + 15) // 16]
+    sh = (2 * (15 - np.arange(16))).astype(np.uint32)
+    return ((w[:, None] >> sh[None, :]) & 3).astype(np.uint8).reshape(-1)[:n_bases]
+
+
 # ----------------------------------------------------------------------------- oracle calls
 def words_s1(k):
     return lib().cx1o_words_s1(k)

@@ -87,6 +87,44 @@ DATASETS = {
 }
 
 
+def assist_fasta(name, directory):
+    """Deterministic `--assist_seq` input for dataset `name` (reference s1.cpp:104-134: FASTA + `<file>.info` holding
+    `num_seq num_bases`): contig-like stretches stitched from the dataset's own reads (forward and reverse complement),
+    with lower case, N, a multi-line layout and one sequence shorter than any k+1.  -> path of the FASTA file."""
+    from oracle import oracle as O
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, name + ".assist.fa")
+    if os.path.exists(path) and os.path.exists(path + ".info"):
+        return path
+    prefix = materialise(name, directory)
+    lens, offs, raw = O.load_bin_records(prefix)
+    bases, start = O.unpack_bases(lens, offs, raw)
+    rng = np.random.default_rng(77)
+    seqs = []
+    n = len(lens)
+    for i in range(9):
+        parts = []
+        for r in rng.integers(0, n, size=int(rng.integers(2, 7))):
+            parts.append(bases[int(start[r]):int(start[r + 1])])
+        a = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+        if i % 3 == 1:
+            a = (3 - a)[::-1]
+        t = list("ACGT"[int(c)] for c in a)
+        for j in rng.integers(0, max(1, len(t)), size=3):
+            if len(t):
+                t[int(j)] = "N" if i % 2 else t[int(j)].lower()
+        seqs.append("".join(t))
+    seqs.append("ACGTNacgtTTGACCA")                      # 16 bases: shorter than k + 1
+    with open(path, "w") as f:
+        for i, q in enumerate(seqs):
+            f.write(">assist_%d some description\n" % i)
+            for o in range(0, len(q), 70):
+                f.write(q[o:o + 70] + "\n")
+    with open(path + ".info", "w") as f:
+        f.write("%d %d\n" % (len(seqs), sum(len(q) for q in seqs)))
+    return path
+
+
 def md5(path):
     h = hashlib.md5()
     with open(path, "rb") as f:

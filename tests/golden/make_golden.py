@@ -35,6 +35,7 @@ for k, m, mercy in [(21, 1, False), (25, 2, False), (25, 2, True)]:
 for k, m, mercy in [(31, 2, False), (61, 2, False), (21, 3, False)]:
     CASES.append(("meta200k", k, m, mercy))
 CASES.append(("meta1m", 31, 2, False))
+ASSIST_CASES = [("smoke", 31, 2), ("smoke", 31, 1), ("adversarial", 27, 3), ("meta200k", 61, 2)]   # --assist_seq
 
 
 def main():
@@ -79,6 +80,28 @@ def main():
             entry["mercy_cand_sha"] = hashlib.sha256(np.sort(cands).tobytes()).hexdigest()[:16]
         golden["cases"][name] = entry
         print(name, entry["total_size"], entry["stream_hash"], entry["meta_hash"], entry.get("num_mercy"), flush=True)
+        for f in os.listdir(work):
+            if f.startswith(name + "."):
+                os.remove(os.path.join(work, f))
+    for ds, k, m in ASSIST_CASES:
+        name = "%s_k%d_m%d_assist" % (ds, k, m)
+        if flt and flt not in name:
+            continue
+        prefix = datasets.materialise(ds, os.path.join(work, "data"))
+        fa = datasets.assist_fasta(ds, os.path.join(work, "data"))
+        golden["datasets"][ds + ".assist.fa"] = datasets.md5(fa)
+        outp = os.path.join(work, name)
+        log = O.run_ref_buildgraph(prefix, outp, k, m, threads=8, assist_seq=fa)
+        hdr, stream, meta = sdbg_io.canonical(outp)
+        nw = re.search(r"\]\s+((?:\d+ ){9})\s*$", log, re.M)
+        entry = dict(dataset=ds, k=k, m=m, mercy=False, assist=True, total_size=hdr["total_size"], num_tips=hdr["num_tips"],
+                     large_multi=hdr["large_multi"], words_per_tip_label=hdr["words_per_tip_label"],
+                     stream_bytes=len(stream), stream_hash=sdbg_io.stream_hash(stream), meta_hash=sdbg_io.meta_hash(meta),
+                     num_w=[int(x) for x in nw.group(1).split()] if nw else None, num_mercy=None)
+        if m > 1:
+            entry["counting_sha"] = hashlib.sha256(open(outp + ".counting", "rb").read()).hexdigest()[:16]
+        golden["cases"][name] = entry
+        print(name, entry["total_size"], entry["stream_hash"], entry["meta_hash"], flush=True)
         for f in os.listdir(work):
             if f.startswith(name + "."):
                 os.remove(os.path.join(work, f))

@@ -272,3 +272,23 @@ def test_gpu_scan_sharded_stage1_exchange(read_lib, ds, k, m, cap):
         finally:
             for c in ctxs:
                 c.close()
+
+
+@pytest.mark.parametrize("ds,k,m", [("smoke", 31, 2), ("smoke", 31, 1), ("adversarial", 27, 3), ("meta200k", 61, 2), ("tiny", 25, 2)])
+def test_gpu_assist_reads_match_oracle(read_lib, data_dir, ds, k, m):
+    """Assist reads (mgta_set_reads n_short_reads < n_reads; reference s1.cpp:104-134, s2.cpp:276,529): they count in
+    stage 1, never get is_solid bits, and all their edges are solid in stage 2."""
+    import datasets
+    _, rd = read_lib(ds)
+    rd2, n_short = O.with_assist(rd, datasets.assist_fasta(ds, data_dir))
+    exp = O.build_graph(rd2, k, m, False, n_short=n_short)
+    with cabi.Context(k, m) as ctx:
+        ctx.set_reads(rd2["seq"], rd2["start"], n_short=n_short, max_len=rd2["max_len"])
+        if m > 1:
+            ec = ctx.stage1()
+            assert np.array_equal(ec, exp["counting"])
+            n = O.solid_bytes(rd2, k, n_short)
+            assert np.array_equal(ctx.get_is_solid()[:n], exp["is_solid"][:n])
+        stream, meta, totals = ctx.stage2()
+    assert stream == exp["stream"]
+    assert np.array_equal(meta, exp["meta"]) and np.array_equal(totals, exp["totals"])

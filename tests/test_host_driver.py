@@ -59,3 +59,34 @@ def test_driver_writes_the_reference_files(case, golden, read_lib, tmp_path):
     if g["m"] > 1:
         txt = open(out + ".counting").read()
         assert hashlib.sha256(txt.encode()).hexdigest()[:16] == g["counting_sha"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["smoke_k31_m2_assist", "smoke_k31_m1_assist", "adversarial_k27_m3_assist", "meta200k_k61_m2_assist"])
+def test_driver_with_assist_seq_writes_the_reference_files(case, golden, read_lib, data_dir, tmp_path):
+    """--assist_seq: the driver loads the FASTA like the reference (reversed, ACGTNacgtn map, .info),
+    the kernels count the assist occurrences and treat their edges as solid; golden = the reference with --assist_seq."""
+    import datasets
+    g = golden["cases"][case]
+    prefix, _ = read_lib(g["dataset"])
+    fa = datasets.assist_fasta(g["dataset"], data_dir)
+    assert datasets.md5(fa) == golden["datasets"][g["dataset"] + ".assist.fa"]
+    out = str(tmp_path / "g")
+    r = run(["-k", str(g["k"]), "-m", str(g["m"]), "--host_mem", "4e9", "--num_cpu_threads", "4", "--num_output_threads", "1",
+             "--read_lib_file", prefix, "--assist_seq", fa, "--output_prefix", out])
+    assert r.returncode == 0, r.stderr
+    hdr, stream, meta = sdbg_io.canonical(out)
+    assert hdr["total_size"] == g["total_size"] and hdr["num_tips"] == g["num_tips"] and hdr["large_multi"] == g["large_multi"]
+    assert len(stream) == g["stream_bytes"]
+    assert O.stream_hash(stream) == g["stream_hash"]
+    assert O.meta_hash(meta) == g["meta_hash"]
+    if g["m"] > 1:
+        txt = open(out + ".counting").read()
+        assert hashlib.sha256(txt.encode()).hexdigest()[:16] == g["counting_sha"]
+
+
+def test_driver_reports_missing_assist_info(tmp_path):
+    fa = tmp_path / "a.fa"
+    fa.write_text(">x\nACGT\n")
+    r = run(["--read_lib_file", str(tmp_path / "nope"), "--assist_seq", str(fa), "--host_mem", "1e9", "--num_cpu_threads", "2"])
+    assert r.returncode == 1 and "[ERROR]" in r.stderr

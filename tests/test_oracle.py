@@ -59,3 +59,21 @@ def test_oracle_histograms_sum_to_item_counts(read_lib):
     _, meta, _ = O.stage2(rd, k, 2, is_solid)
     assert h2.sum() >= meta[:, 0].sum()
     assert np.all((h2 == 0) <= (meta[:, 0] == 0))
+
+
+ASSIST_CASES = ["smoke_k31_m2_assist", "smoke_k31_m1_assist", "adversarial_k27_m3_assist"]
+
+
+@pytest.mark.parametrize("case", ASSIST_CASES)
+def test_oracle_with_assist_reads_matches_reference_golden(case, golden, read_lib, data_dir):
+    """--assist_seq (reference s1.cpp:104-134): the FASTA sequences are appended reversed as always-solid reads that
+    count in stage 1 but get no is_solid bits.  Golden = the unmodified reference binary run with --assist_seq."""
+    import datasets
+    g = golden["cases"][case]
+    _, rd = read_lib(g["dataset"])
+    fa = datasets.assist_fasta(g["dataset"], data_dir)
+    assert datasets.md5(fa) == golden["datasets"][g["dataset"] + ".assist.fa"]
+    rd2, n_short = O.with_assist(rd, fa)
+    assert rd2["n_reads"] == n_short + 10
+    res = O.build_graph(rd2, g["k"], g["m"], False, n_short=n_short)
+    check_against_golden(res, g)
