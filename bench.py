@@ -263,8 +263,9 @@ def main():
             torch.as_tensor(DevBuf(sp + world * per_words * 4, 4), device=dev).fill_(0)             # the spare last word
             h2d = per_words * 4 + a.reads_per_gpu * 8
         elif rank == 0:
-            ctx._check(ctx.lib.mgta_set_reads(ctx.h, seq_pin.data_ptr(), n_words, start_pin.data_ptr(), n_reads, n_reads, L),
-                       "mgta_set_reads")
+            # pinned buffers that outlive the step: the asynchronous upload hides behind the stage-1 extraction
+            ctx._check(ctx.lib.mgta_set_reads_async(ctx.h, seq_pin.data_ptr(), n_words, start_pin.data_ptr(), n_reads, n_reads, L),
+                       "mgta_set_reads_async")
             ctx.n_short, ctx.max_len = n_reads, L
             h2d = n_words * 4 + (n_reads + 1) * 8
         else:

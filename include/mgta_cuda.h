@@ -94,6 +94,14 @@ const char *mgta_last_error(const mgta_ctx *ctx); /* ctx may be NULL: last creat
 int mgta_set_reads(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_t n_words, const uint64_t *start_idx,
                    uint64_t n_reads, uint64_t n_short_reads, int32_t max_read_len);
 
+/* The same, asynchronous: returns once the copies are queued (start_idx first, then packed_seq in chunks on a copy
+ * stream of the context); mgta_stage1 extracts a chunk as soon as the next one has landed, so the upload hides behind
+ * the extraction.  Every other entry point waits for the whole upload.  The host buffers must be pinned
+ * (cudaHostAlloc / cudaHostRegister) and stay valid and unchanged until the next mgta_stage1 / mgta_stage2 /
+ * histogram call on the context has returned; pageable buffers take the synchronous path of mgta_set_reads. */
+int mgta_set_reads_async(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_t n_words, const uint64_t *start_idx,
+                         uint64_t n_reads, uint64_t n_short_reads, int32_t max_read_len);
+
 /* Multi-GPU read distribution (north star: "packed reads are broadcast with NCCL over NVLink"):
  * a non-root shard allocates device buffers of the right size, the caller broadcasts the root's
  * buffers into them (ncclBroadcast / torch.distributed.broadcast) and no host copy is needed.

@@ -36,7 +36,7 @@ class StageStats(ctypes.Structure):
 SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                         ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64))
 
-EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_alloc_reads",
+EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_set_reads_async", "mgta_alloc_reads",
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
            "mgta_stage1_slab_items", "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
@@ -60,6 +60,7 @@ def load():
         lib.mgta_ctx_destroy.restype = None
         lib.mgta_set_reads.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
                                        ctypes.c_uint64, ctypes.c_int32]
+        lib.mgta_set_reads_async.argtypes = lib.mgta_set_reads.argtypes
         lib.mgta_alloc_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.c_int32]
         lib.mgta_reads_device_buffers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
@@ -137,6 +138,13 @@ class Context:
         self._reads = (seq, start)
         self.n_short, self.max_len = n_short, max_len
         self._check(self.lib.mgta_set_reads(self.h, _p(seq), len(seq), _p(start), n, n_short, max_len), "mgta_set_reads")
+
+    def set_reads_async(self, seq_ptr, n_words, start_ptr, n_reads, n_short, max_len):
+        """asynchronous upload from PINNED host memory given by address (the caller keeps the buffers alive and unchanged
+        until the next stage / histogram call has returned); mgta_stage1 pipelines the extraction behind the copy"""
+        self.n_short, self.max_len = n_short, max_len
+        self._check(self.lib.mgta_set_reads_async(self.h, seq_ptr, n_words, start_ptr, n_reads, n_short, max_len),
+                    "mgta_set_reads_async")
 
     def alloc_reads(self, n_words, n_reads, n_short, total_bases, max_len):
         self.n_short, self.max_len = n_short, max_len

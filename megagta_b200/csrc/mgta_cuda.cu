@@ -102,6 +102,13 @@ struct mgta_ctx {
     bool n_positions_valid = false;
     ExchangeState xch;
     uint64_t slab_suggest = 0;             // cached mgta_stage1_slab_items() (0 = not computed for the current reads)
+    // asynchronous upload (mgta_set_reads_async): start_idx first, then packed_seq in chunks on a copy stream; stage 1
+    // extracts chunk c as soon as chunk c + 1 has landed
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
+    std::vector<uint64_t> chunk_end;       // end base of each chunk (multiples of 16384 except the last = total_bases)
+    bool copy_pending = false;
 };
 
 #define CK(call)                                                                                         \
@@ -297,17 +304,33 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
     cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_hist2);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    for (auto e : ctx->ev_chunk) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 namespace {
+// everything but the pipelined stage-1 extraction sees the reads only once the whole upload has landed
+int wait_reads(mgta_ctx *ctx) {
+    if (ctx->copy_pending) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk.back(), 0));
+        ctx->copy_pending = false;
+    }
+    return MGTA_OK;
+}
+
 int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_short, uint64_t total, int max_len) {
     if (n_reads == 0 || n_short > n_reads) FAIL(MGTA_ERR_ARG, "reads: bad counts");
     if (total == 0) FAIL(MGTA_ERR_ARG, "reads: no bases");
     if (n_words * 16 < total) FAIL(MGTA_ERR_ARG, "reads: packed_seq shorter than start_idx says");
     if (total >= (1ull << 40) - 1) FAIL(MGTA_ERR_ARG, "reads: more than 2^40 bases");
     CK(cudaSetDevice(ctx->opt.device));
+    if (ctx->copy_pending) {                                       // a previous asynchronous upload still owns the buffers
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->copy_pending = false;
+    }
     const uint64_t padded = ((n_words + 3) & ~3ull) + SEQ_PAD_WORDS;
     const uint64_t solid_words = (total + 31) / 32 + 4;
     if (n_words != ctx->n_words || n_reads != ctx->n_reads || total != ctx->total_bases || !ctx->d_seq) {     // reuse buffers of equal shape
@@ -345,6 +368,41 @@ extern "C" int mgta_set_reads(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_
     return MGTA_OK;
 }
 
+extern "C" int mgta_set_reads_async(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_t n_words, const uint64_t *start_idx,
+                                    uint64_t n_reads, uint64_t n_short_reads, int32_t max_read_len) {
+    if (!ctx) return MGTA_ERR_ARG;
+    if (!packed_seq || !start_idx || n_reads == 0) FAIL(MGTA_ERR_ARG, "set_reads: bad arguments");
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, packed_seq) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    constexpr int NCH = 8;
+    constexpr uint64_t ALIGN_WORDS = 1024;                         // 16384 bases: a multiple of every extraction tile
+    if (!pinned || n_words < NCH * ALIGN_WORDS * 64)               // pageable memory copies synchronously anyway; tiny inputs
+        return mgta_set_reads(ctx, packed_seq, n_words, start_idx, n_reads, n_short_reads, max_read_len);
+    int rc = alloc_reads(ctx, n_words, n_reads, n_short_reads, start_idx[n_reads], max_read_len);
+    if (rc) return rc;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+        ctx->ev_chunk.resize(NCH);
+        for (auto &e : ctx->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));               // the copies follow the buffer set-up on the main stream
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
+    CK(cudaMemcpyAsync(ctx->d_start, start_idx, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_start, ctx->copy_stream));
+    ctx->chunk_end.assign(NCH, 0);
+    const uint64_t per = ((n_words + NCH - 1) / NCH + ALIGN_WORDS - 1) / ALIGN_WORDS * ALIGN_WORDS;
+    for (int c = 0; c < NCH; ++c) {
+        const uint64_t w0 = std::min<uint64_t>(n_words, (uint64_t)c * per), w1 = c + 1 == NCH ? n_words : std::min<uint64_t>(n_words, w0 + per);
+        if (w1 > w0) CK(cudaMemcpyAsync(ctx->d_seq + w0, packed_seq + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+        ctx->chunk_end[c] = c + 1 == NCH ? ctx->total_bases : std::min<uint64_t>(ctx->total_bases, w1 * 16);
+    }
+    ctx->copy_pending = true;
+    return MGTA_OK;
+}
+
 extern "C" int mgta_alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_short_reads,
                                 uint64_t total_bases, int32_t max_read_len) {
     if (!ctx) return MGTA_ERR_ARG;
@@ -358,6 +416,7 @@ extern "C" int mgta_reads_device_buffers(mgta_ctx *ctx, void **seq_dev, uint64_t
                                          uint64_t *start_bytes) {
     if (!ctx || !seq_dev || !seq_bytes || !start_dev || !start_bytes) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads or mgta_alloc_reads first");
+    if (ctx->copy_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }   // the caller's streams are not ours
     *seq_dev = ctx->d_seq; *seq_bytes = ctx->n_words * 4;
     *start_dev = ctx->d_start; *start_bytes = (ctx->n_reads + 1) * 8;
     return MGTA_OK;
@@ -394,6 +453,7 @@ void set_shard_range(mgta_ctx *ctx, uint64_t total);
 int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     CK(cudaSetDevice(ctx->opt.device));
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     const int W = stage == 1 ? key_words_s1(ctx->opt.kmer_k) : key_words_s2(ctx->opt.kmer_k);
     WalkParams P = walk_params(ctx);
     const unsigned grid = (unsigned)((ctx->total_bases + WALK_TILE - 1) / WALK_TILE);
@@ -478,6 +538,7 @@ size_t hbm_budget(mgta_ctx *ctx) {
 
 int count_positions(mgta_ctx *ctx) {
     if (ctx->n_positions_valid) return MGTA_OK;
+    if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_start, 0));     // start_idx has landed; packed_seq may not have
     CK(cudaMemsetAsync(ctx->d_totals + 13, 0, 8, ctx->stream));
     k_count_positions<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, 0, ctx->n_reads, ctx->opt.kmer_k,
                                                                                      ctx->d_totals + 13);
@@ -852,7 +913,7 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
             EdgePartParams EP;
             memset(&EP, 0, sizeof(EP));
             EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
-            EP.total_bases = ctx->total_bases; EP.k = k;
+            EP.total_bases = ctx->total_bases; EP.k = k; EP.g_begin = 0; EP.g_end = ctx->total_bases;
             EP.filter = cp.stage1_mode ? 0 : 1; EP.all_solid = ctx->opt.min_count == 1; EP.solid = ctx->d_solid;
             EP.sh1 = 32 - (int)cp.lb1; EP.sh2 = 32 - cp.bits; EP.lb2 = cp.lb2; EP.b_lo = b_lo; EP.b_hi = b_hi;
             EP.cursor1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1); EP.slab_cap = L.slab_cap;
@@ -860,10 +921,28 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
             EP.dst = reinterpret_cast<uint32_t *>(ctx->arena + L.A); EP.cap = L.capA;
             EP.err = ctx->d_ctr + CTR_ERR;
             if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
-            if (launch_edge_part(WE, PW, EP, ctx->total_bases, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (ctx->copy_pending && cp.stage1_mode && !cp.mark_mode) {
+                // the upload is still in flight: extract chunk c once chunk c + 1 has landed (a tile stages a few words
+                // past its end), so the copy hides behind the extraction
+                const int nch = (int)ctx->ev_chunk.size();
+                uint64_t g0 = 0;
+                for (int c = 0; c < nch; ++c) {
+                    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[std::min(c + 1, nch - 1)], 0));
+                    EP.g_begin = g0; EP.g_end = ctx->chunk_end[c];
+                    if (EP.g_end > EP.g_begin) {
+                        if (launch_edge_part(WE, PW, EP, EP.g_end - EP.g_begin, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                        st->n_launches++;
+                    }
+                    g0 = EP.g_end;
+                }
+                ctx->copy_pending = false;
+            } else {
+                if ((rc = wait_reads(ctx))) return rc;
+                if (launch_edge_part(WE, PW, EP, ctx->total_bases, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                st->n_launches++;
+            }
             CK(cudaGetLastError());
             if ((rc = end_timed(ctx))) return rc;
-            st->n_launches++;
             bool overflow = false;
             double need = slack;
             if ((rc = count_batch_tail(ctx, cp, L, b_lo, b_hi, n_batches, batch, slack, st, overflow, need))) return rc;
@@ -885,6 +964,7 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
     ExchangeState &X = ctx->xch;
     X.valid = false;
     if (r_begin > r_end || r_end > ctx->n_reads) FAIL(MGTA_ERR_ARG, "stage1_scan: bad read range");
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     const int world = ctx->opt.world;
     if (world > MAX_OWNERS) FAIL(MGTA_ERR_ARG, "stage1_scan: at most %d shards", (int)MAX_OWNERS);
     CountPlan cp;
@@ -1416,6 +1496,7 @@ extern "C" int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items) {
     if (world > MAX_OWNERS) FAIL(MGTA_ERR_ARG, "at most %d shards", (int)MAX_OWNERS);
     if (!ctx->slab_suggest) {
         CK(cudaSetDevice(ctx->opt.device));
+        { int rcw = wait_reads(ctx); if (rcw) return rcw; }
         unsigned long long *d_out = ctx->d_xs;                       // (MAX_OWNERS + 1) * 24 bytes: room for `world` counters
         CK(cudaMemsetAsync(d_out, 0, (size_t)world * 8, ctx->stream));
         k_count_positions_parts<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_reads, ctx->opt.kmer_k,

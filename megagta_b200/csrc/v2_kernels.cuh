@@ -153,7 +153,8 @@ struct EdgePartParams {
     // [owner_lo[d], owner_lo[d + 1]).  Slab d starts at item index d * slab_stride; no tile histogram is taken.
     int n_owner;
     unsigned owner_lo[MAX_OWNERS + 1];
-    uint64_t g_begin, g_end, r_begin;
+    uint64_t g_begin, g_end;        // base range of this launch (g_begin a multiple of 1024); all modes
+    uint64_t r_begin;
     unsigned long long slab_stride;
 };
 
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
     bin_smem_carve(S, smem_raw, IW, TP);
     const int tid = threadIdx.x;
     const int NB = P.n_owner ? P.n_owner : (int)(P.b_hi - P.b_lo);
-    const uint64_t g0 = (P.n_owner ? P.g_begin : 0ull) + (uint64_t)blockIdx.x * TP;
-    const uint64_t gend = min(g0 + (uint64_t)TP, P.n_owner ? P.g_end : P.total_bases);
+    const uint64_t g0 = P.g_begin + (uint64_t)blockIdx.x * TP;    // [g_begin, g_end): the whole read set, a shard's slice of it,
+    const uint64_t gend = min(g0 + (uint64_t)TP, P.g_end);         // or one upload chunk (copy / extract pipeline)
     const uint64_t w_lo = (g0 >> 4) >= WALK_BACK_WORDS ? (g0 >> 4) - WALK_BACK_WORDS : 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.seq + w_lo);

@@ -292,3 +292,28 @@ def test_gpu_assist_reads_match_oracle(read_lib, data_dir, ds, k, m):
         stream, meta, totals = ctx.stage2()
     assert stream == exp["stream"]
     assert np.array_equal(meta, exp["meta"]) and np.array_equal(totals, exp["totals"])
+
+
+def test_gpu_async_upload_pipelined_with_stage1(golden, read_lib):
+    """mgta_set_reads_async from pinned memory: stage 1 extracts chunk c while chunk c + 1 .. are still being copied;
+    a second context takes the pageable (synchronous) fallback; both must reproduce the reference golden."""
+    import torch
+    g = golden["cases"]["meta1m_k31_m2"]
+    _, rd = read_lib(g["dataset"])
+    seq = torch.from_numpy(np.ascontiguousarray(rd["seq"], dtype=np.uint32).view(np.int32)).pin_memory()
+    start = torch.from_numpy(np.ascontiguousarray(rd["start"], dtype=np.uint64).view(np.int64)).pin_memory()
+    n = len(rd["start"]) - 1
+    for pinned in (True, False):
+        with cabi.Context(g["k"], g["m"]) as ctx:
+            if pinned:
+                ctx.set_reads_async(seq.data_ptr(), seq.numel(), start.data_ptr(), n, n, rd["max_len"])
+            else:
+                a, b = seq.numpy().copy(), start.numpy().copy()
+                ctx.set_reads_async(a.ctypes.data, len(a), b.ctypes.data, n, n, rd["max_len"])
+            got = {"counting": ctx.stage1()}
+            assert ctx.stats(1)["n_launches"] >= (14 if pinned else 7)      # 8 extraction launches when pipelined
+            got["stream"], got["meta"], got["totals"] = ctx.stage2()
+            check_vs_golden(got, g)
+            if pinned:                                   # a histogram call right after an asynchronous upload waits for it
+                ctx.set_reads_async(seq.data_ptr(), seq.numel(), start.data_ptr(), n, n, rd["max_len"])
+                assert np.array_equal(ctx.histogram(1), O.s1_hist(rd, g["k"]))
