@@ -167,9 +167,14 @@ int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev
                                  uint64_t *send_counts /* [world] */);
 int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts /* [world] */, int64_t *edge_counting);
 
-/* Mercy candidates of this shard (s1.cpp:762-826): packed ((start_idx+kmer_offset)<<2)|flag.
- * Valid after mgta_stage1 with need_mercy.  *n receives the count; copies min(*n, cap). */
+/* Mercy edges (opts.need_mercy, min_count > 1, world == 1): mgta_stage1 then also (a) emits the mercy candidates of
+ * s1_lv2_output_ (s1.cpp:762-826: packed ((start_idx + kmer_offset) << 2) | flag; the reference spreads them over
+ * <prefix>.mercy_cand.N files, here they stay on the device) and (b) runs the per-read scan of s2_read_mercy_prepare
+ * (s2.cpp:106-250) that extends is_solid; mgta_stage2 then builds the graph from the extended vector.
+ * mgta_get_mercy_candidates: *n receives the count; copies min(*n, cap) values (any order). */
 int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t cap, uint64_t *n);
+/* Number of is_solid bits the per-read mercy scan added (the reference logs it as "Number mercy", s2.cpp:241). */
+int mgta_get_num_mercy(mgta_ctx *ctx, uint64_t *num_mercy);
 
 /* Stage 2 (cx1.run() with the s2 callbacks + SdbgWriter): emits this shard's buckets in ascending
  * order.  sink may be NULL (device-resident run: records are produced and counted, not copied).

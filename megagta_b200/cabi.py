@@ -40,7 +40,7 @@ EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_r
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
            "mgta_stage1_slab_items", "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
-           "mgta_get_mercy_candidates", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
+           "mgta_get_mercy_candidates", "mgta_get_num_mercy", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
            "mgta_edge_hist_device_buffer", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version"]
 
@@ -82,6 +82,7 @@ def load():
         lib.mgta_set_is_solid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
         lib.mgta_get_mercy_candidates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                                   ctypes.POINTER(ctypes.c_uint64)]
+        lib.mgta_get_num_mercy.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_stage2.argtypes = [ctypes.c_void_p, SINK, ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_edges_local.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
                                          ctypes.POINTER(ctypes.c_int32)]
@@ -219,6 +220,11 @@ class Context:
             self._check(self.lib.mgta_get_mercy_candidates(self.h, _p(out), n.value, ctypes.byref(n)),
                         "mgta_get_mercy_candidates")
         return out
+
+    def num_mercy(self):
+        n = ctypes.c_uint64()
+        self._check(self.lib.mgta_get_num_mercy(self.h, ctypes.byref(n)), "mgta_get_num_mercy")
+        return n.value
 
     def stage2(self, collect=True):
         """-> (stream bytes, meta int64[65536,3], totals int64[10]).

@@ -282,7 +282,6 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 int build_graph(int argc, char **argv) {
     const double t0 = now();
     Options opt = parse(argc, argv);
-    if (opt.need_mercy) die("--need_mercy is not supported by the B200 driver yet (SURVEY 8f row 1)");
 
     Reads R = load_read_lib(opt.read_lib_file, opt.num_cpu_threads);
     fprintf(stderr, "[B200] %llu reads, %llu bases, max length %d, loaded in %.2f s\n", (unsigned long long)R.n_reads,
@@ -297,7 +296,7 @@ int build_graph(int argc, char **argv) {
 
     mgta_opts mo;
     memset(&mo, 0, sizeof(mo));
-    mo.kmer_k = opt.kmer_k; mo.min_count = opt.min_count; mo.need_mercy = 0;
+    mo.kmer_k = opt.kmer_k; mo.min_count = opt.min_count; mo.need_mercy = opt.need_mercy && opt.min_count > 1 ? 1 : 0;
     mo.device = 0; mo.rank = 0; mo.world = 1;
     mo.hbm_budget_bytes = (int64_t)opt.gpu_mem;                 // 0 = 90 % of the free HBM, as the reference's "auto detect"
     mgta_ctx *ctx = nullptr;
@@ -317,6 +316,11 @@ int build_graph(int argc, char **argv) {
         long long solid = 0;
         for (int i = opt.min_count; i <= 65535; ++i) solid += ec[i];
         fprintf(stderr, "[B200] Total number of solid edges: %lld\n", solid);
+        if (mo.need_mercy) {                                                       // s2.cpp:241 logs the same figure
+            uint64_t nm = 0;
+            ck(mgta_get_num_mercy(ctx, &nm), "mgta_get_num_mercy");
+            fprintf(stderr, "[B200] Number mercy: %llu\n", (unsigned long long)nm);
+        }
     }
     Writer W;
     W.prefix = opt.output_prefix;

@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "v2_kernels.cuh"
 #include "emit_kernels.cuh"
+#include "mercy_kernels.cuh"
 
 using namespace mgta;
 
@@ -109,6 +110,10 @@ struct mgta_ctx {
     std::vector<cudaEvent_t> ev_chunk;
     std::vector<uint64_t> chunk_end;       // end base of each chunk (multiples of 16384 except the last = total_bases)
     bool copy_pending = false;
+    // mercy (need_mercy): candidates of the last stage 1 and the number of is_solid bits the per-read scan added
+    unsigned long long *d_cand = nullptr;
+    uint64_t cand_cap = 0, n_cand = 0, num_mercy = 0;
+    bool mercy_valid = false;
 };
 
 #define CK(call)                                                                                         \
@@ -132,18 +137,18 @@ struct mgta_ctx {
 
 namespace {
 
-#define W_SWITCH(W, STMT)                                   \
-    switch (W) {                                            \
-        case 1: { constexpr int WW = 1; STMT; } break;      \
-        case 2: { constexpr int WW = 2; STMT; } break;      \
-        case 3: { constexpr int WW = 3; STMT; } break;      \
-        case 4: { constexpr int WW = 4; STMT; } break;      \
-        case 5: { constexpr int WW = 5; STMT; } break;      \
-        case 6: { constexpr int WW = 6; STMT; } break;      \
-        case 7: { constexpr int WW = 7; STMT; } break;      \
-        case 8: { constexpr int WW = 8; STMT; } break;      \
-        case 9: { constexpr int WW = 9; STMT; } break;      \
-        default: break;                                     \
+#define W_SWITCH(W, ...)                                           \
+    switch (W) {                                                   \
+        case 1: { constexpr int WW = 1; __VA_ARGS__; } break;      \
+        case 2: { constexpr int WW = 2; __VA_ARGS__; } break;      \
+        case 3: { constexpr int WW = 3; __VA_ARGS__; } break;      \
+        case 4: { constexpr int WW = 4; __VA_ARGS__; } break;      \
+        case 5: { constexpr int WW = 5; __VA_ARGS__; } break;      \
+        case 6: { constexpr int WW = 6; __VA_ARGS__; } break;      \
+        case 7: { constexpr int WW = 7; __VA_ARGS__; } break;      \
+        case 8: { constexpr int WW = 8; __VA_ARGS__; } break;      \
+        case 9: { constexpr int WW = 9; __VA_ARGS__; } break;      \
+        default: break;                                            \
     }
 
 template <int STAGE, int MODE>
@@ -302,7 +307,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
-    cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs);
+    cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs); cudaFree(ctx->d_cand);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_hist2);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -1122,6 +1127,178 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
     return MGTA_OK;
 }
 
+// ---- mercy edges (need_mercy) ------------------------------------------------------------------------
+// stage-1 items of the reference (s1_position) -> hash partition by (k-1)-mer -> per-tile tables -> candidates
+// (s1.cpp:671-830); then candidates -> position bit vectors -> per-read scan adding is_solid bits (s2.cpp:106-250).
+template <int TP>
+int launch_ctx_part_t(int W, const CtxPartParams &P, unsigned grid, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    W_SWITCH(W, {
+        const size_t smem = bin_smem_bytes(WW + 2, 2 * TP);
+        e = cudaFuncSetAttribute(k_ctx_part<WW, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k_ctx_part<WW, TP><<<grid, PART_THREADS, smem, st>>>(P);
+    });
+    return e == cudaSuccess ? 0 : -1;
+}
+
+int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
+    const int k = ctx->opt.kmer_k;
+    const int W = key_words_s1(k), IW = W + 2;
+    int rc = count_positions(ctx);
+    if (rc) return rc;
+    if ((rc = wait_reads(ctx))) return rc;
+    ctx->mercy_valid = false;
+    ctx->n_cand = 0; ctx->num_mercy = 0;
+    const uint64_t n_items_max = ctx->n_positions + 4 * ctx->n_reads;      // L - k + 4 per read with L >= k + 1
+    if (ctx->n_positions == 0) { ctx->mercy_valid = true; return MGTA_OK; }
+    // table: as many slots as one CTA can hold; tiles of mean <= cap / 2 ITEMS can never hold more than tab_limit distinct keys
+    unsigned tab_cap = 4096;
+    while (tab_cap > 256 && mercy_smem_bytes(W, tab_cap) > 200 * 1024) tab_cap >>= 1;
+    const unsigned tab_limit = tab_cap - 600;
+    int bits = 2;
+    while (bits < 30 && (n_items_max >> bits) > tab_cap / 2) ++bits;
+    const unsigned lb2 = (unsigned)std::min(10, bits / 2), lb1 = (unsigned)bits - lb2, B1 = 1u << lb1;
+    const unsigned T = split_chunk_items(IW);
+    const int TP = IW <= 5 ? 2048 : 1024;
+    const size_t budget = hbm_budget(ctx);
+    const size_t vec_bytes = (((ctx->total_bases + 31) / 32 + 4) * 4 + 255) & ~(size_t)255;     // one position bit vector
+    double slack = 1.25;
+    uint64_t cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1 << 20, n_items_max / 8));
+    for (int attempt = 0;; ++attempt) {
+        if (attempt >= 8) FAIL(MGTA_ERR_MEM, "mercy: the partition does not settle");
+        if (cand_cap > ctx->cand_cap) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_cand);
+            ctx->d_cand = nullptr; ctx->cand_cap = 0;
+            CK(cudaMalloc(&ctx->d_cand, cand_cap * 8));
+            ctx->cand_cap = cand_cap;
+        }
+        CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));                            // candidate counter
+        bool retry = false;
+        unsigned n_batches = (B1 + MAX_BINS - 1) / MAX_BINS;
+        struct { size_t A, B, hist2, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, total; uint64_t slab_cap, capA, capB; unsigned bins, NT; } L;
+        auto layout = [&](unsigned nb) {
+            L.bins = (B1 + nb - 1) / nb;
+            L.NT = L.bins << lb2;
+            L.slab_cap = ((uint64_t)((double)n_items_max / B1 * slack) + 2048 + 31) & ~(uint64_t)31;
+            L.capA = L.slab_cap * L.bins;
+            L.capB = std::min<uint64_t>(L.capA, (n_items_max + 31) & ~(uint64_t)31);
+            Carver c;
+            L.A = c.take((size_t)IW * L.capA * 4); L.B = c.take((size_t)IW * L.capB * 4);
+            L.hist2 = c.take((size_t)L.NT * 4); L.loc = c.take((size_t)L.NT * 4);
+            L.off2 = c.take(((size_t)L.NT + 1) * 8); L.cur2 = c.take((size_t)L.NT * 8);
+            L.tot = c.take((MAX_BINS + 1) * 8); L.base = c.take((MAX_BINS + 1) * 8); L.in_start = c.take((MAX_BINS + 1) * 8);
+            L.chunk_pref = c.take((MAX_BINS + 1) * 4); L.cur1 = c.take((MAX_BINS + 1) * 8);
+            L.total = c.o;
+        };
+        layout(n_batches);
+        while (L.total + 3 * vec_bytes > budget && L.bins > 1) { n_batches *= 2; layout(n_batches); }
+        if (L.total + 3 * vec_bytes > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 bin of mercy items (%zu B)", budget, L.total);
+        if ((rc = ensure_arena(ctx, L.total + 3 * vec_bytes))) return rc;
+        const size_t smem_m = mercy_smem_bytes(W, tab_cap);
+        for (unsigned batch = 0; batch < n_batches && !retry; ++batch) {
+            const unsigned b_lo = batch * L.bins, b_hi = std::min(B1, b_lo + L.bins);
+            if (b_lo >= b_hi) break;
+            uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
+            uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+            unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+            unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
+            CK(cudaMemsetAsync(hist2, 0, (size_t)L.NT * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+            k_init_slab_cursors<<<(b_hi - b_lo + 255) / 256, 256, 0, ctx->stream>>>(cur1, b_hi - b_lo, L.slab_cap);
+            CK(cudaGetLastError());
+            CtxPartParams XP0;
+            memset(&XP0, 0, sizeof(XP0));
+            XP0.seq = ctx->d_seq; XP0.start = ctx->d_start; XP0.n_reads = ctx->n_reads; XP0.n_short = ctx->n_short;
+            XP0.total_bases = ctx->total_bases; XP0.k = k; XP0.sh1 = 32 - (int)lb1; XP0.sh2 = 32 - bits; XP0.lb2 = lb2;
+            XP0.b_lo = b_lo; XP0.b_hi = b_hi; XP0.cursor1 = cur1; XP0.slab_cap = L.slab_cap; XP0.hist2 = hist2; XP0.dst = bufA;
+            XP0.cap = L.capA; XP0.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
+            const unsigned grid = (unsigned)((ctx->total_bases + TP - 1) / TP);
+            if (TP == 2048 ? launch_ctx_part_t<2048>(W, XP0, grid, ctx->stream) : launch_ctx_part_t<1024>(W, XP0, grid, ctx->stream))
+                FAIL(MGTA_ERR_CUDA, "k_ctx_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            if ((rc = end_timed(ctx))) return rc;
+            ScanParams SP;
+            memset(&SP, 0, sizeof(SP));
+            const unsigned NTb = (b_hi - b_lo) << lb2;
+            SP.hist = hist2; SP.NT = NTb; SP.lb2 = lb2; SP.t_lo = 0; SP.t_hi = NTb;
+            SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
+            SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
+            SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
+            SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
+            SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
+            SP.T = T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
+            SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
+            if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
+            if ((rc = launch_scans(ctx, SP))) return rc;
+            SplitParams XP;
+            memset(&XP, 0, sizeof(XP));
+            XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = IW; XP.WE = W; XP.mode = 0;
+            XP.drop_last = ~S1_FLAG_MASK;
+            XP.sh2 = 32 - bits; XP.lb2 = lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
+            XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = T; XP.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = launch_split(ctx, XP))) return rc;
+            if ((rc = end_timed(ctx))) return rc;
+            MercyParams MP;
+            memset(&MP, 0, sizeof(MP));
+            MP.src = bufB; MP.cap = L.capB; MP.off2 = off2; MP.t_lo = 0; MP.t_hi = NTb; MP.ticket = ctx->d_ctr + CTR_TICKET2;
+            MP.tab_cap = tab_cap; MP.tab_limit = tab_limit; MP.m = (unsigned)std::min(ctx->opt.min_count, 255);
+            MP.cand_out = ctx->d_cand; MP.n_cand = ctx->d_totals + 11; MP.cand_cap = ctx->cand_cap; MP.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = begin_timed(ctx, PH_SORT))) return rc;
+            {
+                cudaError_t e = cudaSuccess;
+                W_SWITCH(W, {
+                    e = cudaFuncSetAttribute(k_mercy<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+                    if (e == cudaSuccess) k_mercy<WW><<<(unsigned)ctx->sm_count, COUNT_THREADS, smem_m, ctx->stream>>>(MP);
+                });
+                if (e != cudaSuccess) FAIL(MGTA_ERR_CUDA, "k_mercy launch failed: %s", cudaGetErrorString(e));
+            }
+            CK(cudaGetLastError());
+            if ((rc = end_timed(ctx))) return rc;
+            st->n_launches += 6;
+            unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+            CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const unsigned dev_err = h_ctr[CTR_ERR];
+            if (dev_err & ERR_SLAB_OVERFLOW) {
+                std::vector<unsigned long long> hc(b_hi - b_lo);
+                CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long mx = 0;
+                for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
+                slack = std::max(slack * 1.5, (double)mx / ((double)n_items_max / B1) * 1.05);
+                retry = true;
+                break;
+            }
+            if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (mercy pipeline, bins [%u,%u))", dev_err, b_lo, b_hi);
+        }
+        if (retry) continue;
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const uint64_t n_cand = ctx->h_pin[0];
+        if (n_cand > ctx->cand_cap) { cand_cap = n_cand + n_cand / 16 + 1024; continue; }     // counted past the end: rerun with room
+        ctx->n_cand = n_cand;
+        // ---- candidates -> position bit vectors -> per-read scan (s2.cpp:106-250)
+        uint32_t *v_in = reinterpret_cast<uint32_t *>(ctx->arena + L.total), *v_out = reinterpret_cast<uint32_t *>(ctx->arena + L.total + vec_bytes),
+                 *v_any = reinterpret_cast<uint32_t *>(ctx->arena + L.total + 2 * vec_bytes);
+        CK(cudaMemsetAsync(v_in, 0, 3 * vec_bytes, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));
+        if (n_cand) {
+            k_mercy_bits<<<(unsigned)((n_cand + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cand, n_cand, v_in, v_out, v_any);
+            k_mercy_reads<<<(unsigned)((ctx->n_short + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_short, k, v_in, v_out, v_any,
+                                                                                        ctx->d_solid, ctx->d_totals + 11);
+            CK(cudaGetLastError());
+            st->n_launches += 2;
+        }
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->num_mercy = ctx->h_pin[0];
+        break;
+    }
+    ctx->mercy_valid = true;
+    return MGTA_OK;
+}
+
 // is_solid is derived lazily: the hot path (stage 1 -> edge list -> stage 2) never reads it
 int ensure_solid(mgta_ctx *ctx) {
     if (ctx->solid_valid || !ctx->stage1_done || ctx->opt.min_count == 1) return MGTA_OK;
@@ -1455,16 +1632,26 @@ extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
         memset(&ctx->stats[0], 0, sizeof(ctx->stats[0]));
         return MGTA_OK;
     }
-    if (ctx->opt.need_mercy) FAIL(MGTA_ERR_ARG, "need_mercy is not implemented on the device yet");
+    if (ctx->opt.need_mercy && ctx->opt.world > 1) FAIL(MGTA_ERR_ARG, "need_mercy runs on one shard only (world == 1)");
+    if (ctx->opt.need_mercy && ctx->opt.min_count > 255) FAIL(MGTA_ERR_ARG, "need_mercy is offered for min_count <= 255");
     mgta_stage_stats *st = &ctx->stats[0];
     StageTimer tm;
     int rc = stage_begin(ctx, st, tm);
     if (rc) return rc;
     ctx->solid_valid = false;
     ctx->stage1_done = false;
+    ctx->mercy_valid = false;
     if ((rc = run_count(ctx, CM_STAGE1, st))) return rc;
     ctx->stage1_done = true;
     st->n_edges = ctx->n_edges;                                    // distinct solid edges listed for stage 2
+    if (ctx->opt.need_mercy) {
+        // mercy edges extend is_solid read by read (s2.cpp:106-250): derive the vector, add the mercy bits, and let stage 2
+        // recount the solid occurrences from it (the edge list above no longer describes them)
+        if ((rc = ensure_solid(ctx))) return rc;
+        if ((rc = run_mercy(ctx, st))) return rc;
+        ctx->edges_valid = false;
+        ctx->edges_all_valid = false;
+    }
     if (edge_counting) {
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1627,9 +1814,23 @@ extern "C" int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_
 
 extern "C" int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t cap, uint64_t *n) {
     if (!ctx || !n) return MGTA_ERR_ARG;
-    (void)host; (void)cap;
     *n = 0;
-    FAIL(MGTA_ERR_ARG, "need_mercy is not implemented on the device yet");
+    if (!ctx->mercy_valid) FAIL(MGTA_ERR_STATE, "no mercy candidates: run mgta_stage1 with need_mercy first");
+    *n = ctx->n_cand;
+    const uint64_t take = std::min<uint64_t>(cap, ctx->n_cand);
+    if (host && take) {
+        CK(cudaSetDevice(ctx->opt.device));
+        CK(cudaMemcpyAsync(host, ctx->d_cand, take * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return MGTA_OK;
+}
+
+extern "C" int mgta_get_num_mercy(mgta_ctx *ctx, uint64_t *num_mercy) {
+    if (!ctx || !num_mercy) return MGTA_ERR_ARG;
+    if (!ctx->mercy_valid) FAIL(MGTA_ERR_STATE, "no mercy result: run mgta_stage1 with need_mercy first");
+    *num_mercy = ctx->num_mercy;
+    return MGTA_OK;
 }
 
 extern "C" int mgta_edges_local(mgta_ctx *ctx, void **dev, uint64_t *n_rows, int32_t *row_words) {

@@ -376,6 +376,7 @@ struct SplitParams {
     unsigned b_lo, b_hi;
     unsigned long long slab_cap;
     uint32_t *hist2;
+    uint32_t drop_last;                  // bits of the last hashed key word that do not take part in the hash (mercy items: head/tail flags)
 };
 
 __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
             uint32_t x;
             if (P.mode != 1) {
                 uint32_t hb;
-                edge_hash([&](int w) { return S.stage[w * T + i]; }, P.WE, x, hb);
+                edge_hash([&](int w) { const uint32_t v = S.stage[w * T + i]; return w == P.WE - 1 ? v & ~P.drop_last : v; }, P.WE, x, hb);
             } else {
                 x = S.stage[i];
             }

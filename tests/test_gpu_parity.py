@@ -317,3 +317,46 @@ def test_gpu_async_upload_pipelined_with_stage1(golden, read_lib):
             if pinned:                                   # a histogram call right after an asynchronous upload waits for it
                 ctx.set_reads_async(seq.data_ptr(), seq.numel(), start.data_ptr(), n, n, rd["max_len"])
                 assert np.array_equal(ctx.histogram(1), O.s1_hist(rd, g["k"]))
+
+
+MERCY_CASES = ["tiny_k25_m2_mercy", "smoke_k31_m2_mercy", "smoke_k27_m3_mercy", "xander_k29_m2_mercy",
+               "adversarial_k31_m2_mercy", "adversarial_k27_m3_mercy"]
+
+
+@pytest.mark.parametrize("case", MERCY_CASES)
+def test_gpu_mercy_matches_reference_golden_and_oracle(case, golden, read_lib):
+    """--need_mercy on the device: candidate multiset (s1.cpp:762-826), "Number mercy" and the extended
+    is_solid of s2_read_mercy_prepare (s2.cpp:106-250), and the SdBG built from it, against the goldens the unmodified
+    reference produced with --need_mercy and against the oracle."""
+    g = golden["cases"][case]
+    _, rd = read_lib(g["dataset"])
+    k, m = g["k"], g["m"]
+    exp = O.build_graph(rd, k, m, True)
+    with cabi.Context(k, m, need_mercy=True) as ctx:
+        ctx.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+        got = {"counting": ctx.stage1()}
+        cands = ctx.mercy_candidates()
+        assert len(cands) == g["mercy_cand_n"]
+        assert hashlib.sha256(np.sort(cands).astype("<u8").tobytes()).hexdigest()[:16] == g["mercy_cand_sha"]
+        assert ctx.num_mercy() == g["num_mercy"]
+        n = O.solid_bytes(rd, k)
+        assert np.array_equal(ctx.get_is_solid()[:n], exp["is_solid"][:n])
+        got["stream"], got["meta"], got["totals"] = ctx.stage2()
+    check_vs_golden(got, g)
+    assert got["stream"] == exp["stream"]
+
+
+def test_gpu_mercy_with_small_budget_and_bigger_input(golden, read_lib):
+    """mercy over several batches of level-1 bins (small HBM budget) on 200k reads: equal to the oracle"""
+    _, rd = read_lib("meta200k")
+    k, m = 31, 2
+    exp = O.build_graph(rd, k, m, True)
+    ref_c = O.stage1(rd, k, m, True)[2]
+    for budget in (0, 96 << 20):
+        with cabi.Context(k, m, need_mercy=True, hbm_budget_bytes=budget) as ctx:
+            ctx.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+            ctx.stage1()
+            assert np.array_equal(np.sort(ctx.mercy_candidates()), np.sort(ref_c))
+            assert ctx.num_mercy() == exp["num_mercy"]
+            stream, meta, totals = ctx.stage2()
+        assert stream == exp["stream"] and np.array_equal(meta, exp["meta"])

@@ -90,3 +90,18 @@ def test_driver_reports_missing_assist_info(tmp_path):
     fa.write_text(">x\nACGT\n")
     r = run(["--read_lib_file", str(tmp_path / "nope"), "--assist_seq", str(fa), "--host_mem", "1e9", "--num_cpu_threads", "2"])
     assert r.returncode == 1 and "[ERROR]" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["smoke_k31_m2_mercy", "adversarial_k27_m3_mercy", "xander_k29_m2_mercy"])
+def test_driver_with_need_mercy_writes_the_reference_files(case, golden, read_lib, tmp_path):
+    g = golden["cases"][case]
+    prefix, _ = read_lib(g["dataset"])
+    out = str(tmp_path / "g")
+    r = run(["-k", str(g["k"]), "-m", str(g["m"]), "--host_mem", "4e9", "--num_cpu_threads", "4", "--num_output_threads", "1",
+             "--read_lib_file", prefix, "--output_prefix", out, "--need_mercy"])
+    assert r.returncode == 0, r.stderr
+    hdr, stream, meta = sdbg_io.canonical(out)
+    assert hdr["total_size"] == g["total_size"] and hdr["num_tips"] == g["num_tips"]
+    assert O.stream_hash(stream) == g["stream_hash"] and O.meta_hash(meta) == g["meta_hash"]
+    assert "Number mercy: %d" % g["num_mercy"] in r.stderr
