@@ -1664,7 +1664,7 @@ extern "C" int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t rea
     if (!ctx || !needed) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     if (ctx->opt.min_count == 1) FAIL(MGTA_ERR_STATE, "stage1_scan: min_count == 1 has no stage 1");
-    if (ctx->opt.need_mercy) FAIL(MGTA_ERR_ARG, "need_mercy is not implemented on the device yet");
+    if (ctx->opt.need_mercy) FAIL(MGTA_ERR_ARG, "need_mercy runs on one shard only (mgta_stage1 with world == 1)");
     if (ctx->n_short < ctx->n_reads) FAIL(MGTA_ERR_ARG, "stage1_scan: assist reads take the replicated scan (mgta_stage1)");
     mgta_stage_stats *st = &ctx->stats[0];
     StageTimer tm;
