@@ -126,47 +126,88 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons of the job's GPUs during the timed region, sampled by rank 0 only, 4 times a second,
-    through NVML in-process (pynvml).  Measured: one nvidia-smi spawn per rank every 100 ms slowed the 2-GPU step from
-    246 to 304 ms, and even in-process NVML at 20 Hz on every rank cost the 4-GPU step 15 % (the queries serialise with
-    the other processes' driver calls).  nvidia-smi (2 Hz) remains the fallback when the binding is missing."""
-    REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
-
-    def __init__(self, devs):
-        super().__init__(daemon=True)
-        self.devs, self.stop_flag, self.rows, self.max_mhz, self.source = list(devs), False, [], None, "nvidia-smi"
-        self.nvml, self.handles = None, []
+SAMPLER_CHILD = r"""
+import sys, time
+uuids = sys.argv[1:]
+try:
+    import pynvml as n
+    n.nvmlInit()
+    hs = []
+    for i, u in enumerate(uuids):
         try:
-            import pynvml
-            import torch
-            pynvml.nvmlInit()
-            for d in self.devs:
-                try:
-                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(d).uuid)).encode())
-                except Exception:
-                    h = pynvml.nvmlDeviceGetHandleByIndex(d)
-                self.handles.append(h)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handles[0], pynvml.NVML_CLOCK_SM))
-            self.nvml, self.source = pynvml, "nvml"
+            hs.append(n.nvmlDeviceGetHandleByUUID(u.encode()))
         except Exception:
-            self.nvml, self.handles = None, []
-
-    def sample_nvml(self):
-        n = self.nvml
-        for h in self.handles:
+            hs.append(n.nvmlDeviceGetHandleByIndex(i))
+    print("max", int(n.nvmlDeviceGetMaxClockInfo(hs[0], n.NVML_CLOCK_SM)), flush=True)
+    while True:
+        for h in hs:
             sm = int(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
             try:
                 mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
             except Exception:
                 mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-            self.rows.append((sm, mask))
+            print("s", time.time(), sm, mask, flush=True)
+        time.sleep(0.2)
+except Exception as e:
+    print("err", repr(e), flush=True)
+"""
+
+
+class ClockSampler:
+    """SM clock + throttle reasons of the job's GPUs during the timed region, sampled 5 times a second by ONE helper
+    process of rank 0 through NVML.  It is a separate process on purpose: measured on this path, one nvidia-smi spawn per
+    rank every 100 ms slowed the 2-GPU step from 246 to 304 ms, and an in-process NVML thread left 17-34 ms of host gaps in
+    stage 2 (1-2 ms without it) -- the queries serialise with the process's own driver calls.  nvidia-smi (one query
+    before and one after) is the fallback when the binding is missing."""
+    REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+
+    def __init__(self, devs):
+        import torch
+        self.devs, self.rows, self.max_mhz, self.source = list(devs), [], None, "nvml (helper process)"
+        uuids = []
+        for d in self.devs:
+            try:
+                uuids.append("GPU-" + str(torch.cuda.get_device_properties(d).uuid))
+            except Exception:
+                uuids.append("")
+        self.t0 = self.t1 = None
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_CHILD] + uuids, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+        except Exception:
+            self.proc = None
+
+    def start(self):
+        self.t0 = time.time()
+
+    def join(self):
+        self.t1 = time.time()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                out = self.proc.communicate(timeout=5)[0]
+            except Exception:
+                out = ""
+            for line in out.splitlines():
+                f = line.split()
+                if f and f[0] == "max":
+                    self.max_mhz = int(f[1])
+                elif f and f[0] == "s" and self.t0 <= float(f[1]) <= self.t1:
+                    self.rows.append((int(f[2]), int(f[3])))
+        if not self.rows:
+            self.sample_smi()
+
+    stop_flag = False
 
     def sample_smi(self):
+        self.source = "nvidia-smi (after the timed region)"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        o = subprocess.run(["nvidia-smi", "-i", ",".join(str(d) for d in self.devs), "--query-gpu=" + q,
-                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        try:
+            o = subprocess.run(["nvidia-smi", "-i", ",".join(str(d) for d in self.devs), "--query-gpu=" + q,
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        except Exception:
+            o = ""
         for line in o.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 6 and f[0].isdigit():
@@ -174,17 +215,6 @@ class ClockSampler(threading.Thread):
                     self.max_mhz = int(f[1])
                 mask = sum(bit for (bit, _), v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active"))
                 self.rows.append((int(f[0]), mask))
-
-    def run(self):
-        while not self.stop_flag:
-            try:
-                if self.nvml:
-                    self.sample_nvml()
-                else:
-                    self.sample_smi()
-            except Exception:
-                pass
-            time.sleep(0.25 if self.nvml else 0.5)
 
     def summary(self):
         if not self.rows:
@@ -332,11 +362,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / reps, outs
 
+    sampler = ClockSampler(range(world)) if rank == 0 else None         # rank 0 watches all GPUs of the job (one node);
+    if os.environ.get("MGTA_BENCH_SAMPLER") == "off":                   # started here so that it is up before the timed region
+        sampler = None                                                  # (off: diagnostic only)
     with torch.cuda.stream(stream):
         load_reads()
         for _ in range(a.warmup):
             step(False)
-        sampler = ClockSampler(range(world)) if rank == 0 else None     # rank 0 watches all GPUs of the job (one node)
         if sampler:
             sampler.start()
         ms_dev, outs = timed(lambda: step(False), a.steps)
@@ -433,7 +465,7 @@ def main():
                            "gen_seconds": gen_s},
                 "e2e": {"value": edges / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+                "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None, "roofline": roofline,
                 "stage_ms": {"s1": st1["ms_total"], "s2": st2["ms_total"]},
                 "stats": {"s1": st1, "s2": st2}}
         if cpu_baseline:

@@ -116,6 +116,20 @@ struct mgta_ctx {
     bool mercy_valid = false;
 };
 
+// Host waits on the context's stream.  A blocking cudaStreamSynchronize puts the thread to sleep; on a loaded host the
+// wake-up can cost milliseconds while the GPU sits idle, and a step has ~8 such points.  Polling keeps the thread hot.
+static inline cudaError_t mgta_stream_wait(cudaStream_t s) {
+    static const int spin = [] { const char *e = getenv("MGTA_SPIN_SYNC"); return e ? atoi(e) : 1; }();
+    if (!spin) return cudaStreamSynchronize(s);
+    cudaError_t e;
+    while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return e;
+}
+
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -303,7 +317,7 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
 extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->opt.device);
-    cudaStreamSynchronize(ctx->stream);
+    mgta_stream_wait(ctx->stream);
     cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
@@ -369,7 +383,7 @@ extern "C" int mgta_set_reads(mgta_ctx *ctx, const uint32_t *packed_seq, uint64_
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_seq, packed_seq, n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_start, start_idx, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     return MGTA_OK;
 }
 
@@ -413,7 +427,7 @@ extern "C" int mgta_alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_read
     if (!ctx) return MGTA_ERR_ARG;
     int rc = alloc_reads(ctx, n_words, n_reads, n_short_reads, total_bases, max_read_len);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     return MGTA_OK;
 }
 
@@ -473,7 +487,7 @@ int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     if (st) st->n_launches++;
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_hist, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_pin + NUM_BUCKETS, ctx->d_totals + 12, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     if (stage == 2) ctx->n_dollar = ctx->h_pin[NUM_BUCKETS];
     ctx->hist.assign(NUM_BUCKETS, 0);
     uint64_t total = 0;
@@ -525,7 +539,7 @@ struct Carver {
 
 int ensure_arena(mgta_ctx *ctx, size_t bytes) {
     if (bytes > ctx->arena_bytes) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         cudaFree(ctx->arena);
         ctx->arena = nullptr; ctx->arena_bytes = 0;
         CK(cudaMalloc(&ctx->arena, bytes));
@@ -549,7 +563,7 @@ int count_positions(mgta_ctx *ctx) {
                                                                                      ctx->d_totals + 13);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 13, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     ctx->n_positions = ctx->h_pin[0];
     ctx->n_positions_valid = true;
     return MGTA_OK;
@@ -736,11 +750,11 @@ void count_layout(const CountPlan &cp, CountLay &L, unsigned nb, double slack, s
 int ensure_arena_keep(mgta_ctx *ctx, size_t bytes, size_t keep) {
     if (bytes <= ctx->arena_bytes) return MGTA_OK;
     if (!keep || !ctx->arena) return ensure_arena(ctx, bytes);
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     unsigned char *na = nullptr;
     CK(cudaMalloc(&na, bytes));
     CK(cudaMemcpyAsync(na, ctx->arena, std::min(keep, ctx->arena_bytes), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     cudaFree(ctx->arena);
     ctx->arena = na; ctx->arena_bytes = bytes;
     return MGTA_OK;
@@ -825,7 +839,7 @@ int count_batch_tail(mgta_ctx *ctx, const CountPlan &cp, const CountLay &L, unsi
     CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_ne, ctx->d_totals + 14, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_ne + 1, off2 + NTb, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     const unsigned dev_err = h_ctr[CTR_ERR];
     if (dev_err & ERR_SLAB_OVERFLOW) {                    // this batch was not counted (k_split / k_count bail out)
         std::vector<unsigned long long> hc(b_hi - b_lo);   // the cursors kept counting past the slab ends: exact bin sizes
@@ -848,7 +862,7 @@ int count_batch_tail(mgta_ctx *ctx, const CountPlan &cp, const CountLay &L, unsi
             uint32_t *nbuf = nullptr;
             CK(cudaMalloc(&nbuf, ncap * row));
             if (ctx->n_edges) CK(cudaMemcpyAsync(nbuf, ctx->d_edges, ctx->n_edges * row, cudaMemcpyDeviceToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(mgta_stream_wait(ctx->stream));
             cudaFree(ctx->d_edges);
             ctx->d_edges = nbuf; ctx->edges_cap = ncap;
         }
@@ -987,7 +1001,7 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 13, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_pin + 1, ctx->d_start + r_begin, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_pin + 2, ctx->d_start + r_end, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         n_local = ctx->h_pin[0]; g_begin = ctx->h_pin[1]; g_end = ctx->h_pin[2];
     }
     std::vector<unsigned> owner_lo(world + 1);
@@ -1037,7 +1051,7 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
         unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
         CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_pin, cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         X.send_counts.assign(world, 0);
         uint64_t mx = 0;
         for (int d = 0; d < world; ++d) { X.send_counts[d] = ctx->h_pin[d] - (unsigned long long)d * stride; mx = std::max(mx, X.send_counts[d]); }
@@ -1167,7 +1181,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
     for (int attempt = 0;; ++attempt) {
         if (attempt >= 8) FAIL(MGTA_ERR_MEM, "mercy: the partition does not settle");
         if (cand_cap > ctx->cand_cap) {
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(mgta_stream_wait(ctx->stream));
             cudaFree(ctx->d_cand);
             ctx->d_cand = nullptr; ctx->cand_cap = 0;
             CK(cudaMalloc(&ctx->d_cand, cand_cap * 8));
@@ -1259,7 +1273,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
             st->n_launches += 6;
             unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
             CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(mgta_stream_wait(ctx->stream));
             const unsigned dev_err = h_ctr[CTR_ERR];
             if (dev_err & ERR_SLAB_OVERFLOW) {
                 std::vector<unsigned long long> hc(b_hi - b_lo);
@@ -1274,7 +1288,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
         }
         if (retry) continue;
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         const uint64_t n_cand = ctx->h_pin[0];
         if (n_cand > ctx->cand_cap) { cand_cap = n_cand + n_cand / 16 + 1024; continue; }     // counted past the end: rerun with room
         ctx->n_cand = n_cand;
@@ -1291,7 +1305,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
             st->n_launches += 2;
         }
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         ctx->num_mercy = ctx->h_pin[0];
         break;
     }
@@ -1334,7 +1348,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     // tile histogram -> host: lv1 bucket sizes, shard range, batches
     const uint32_t *h2 = ctx->h_hist2;
     CK(cudaMemcpyAsync(ctx->h_hist2, ctx->d_hist_s2, (size_t)NT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     ctx->hist.assign(NUM_BUCKETS, 0);
     uint64_t total = 0;
     for (unsigned t = 0; t < NT; ++t) { ctx->hist[t >> (PB - 16)] += h2[t]; total += h2[t]; }
@@ -1546,7 +1560,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         unsigned long long *h_state = ctx->h_pin + 2 * NUM_BUCKETS + 8;
         CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_state, ctx->d_totals + 15, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         st->n_giants += h_ctr[CTR_NGIANTS] + h_ctr[CTR_NOVF];      // windows sorted by the LSD passes (low-complexity or forced)
         const unsigned dev_err = h_ctr[CTR_ERR];
         if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage 2, buckets [%d,%d))", dev_err, b0, b1);
@@ -1562,13 +1576,13 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
             meta_host.resize((size_t)(b1 - b0) * 3);
             if (bytes) CK(cudaMemcpyAsync(ctx->h_out, outbuf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(meta_host.data(), ctx->d_meta + (size_t)b0 * 3, (size_t)(b1 - b0) * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(mgta_stream_wait(ctx->stream));
             if (sink(user, b0, b1, ctx->h_out, bytes, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
         }
         b0 = b1;
     }
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals, 10 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     uint64_t edges = 0;
     for (int i = 0; i < 9; ++i) edges += ctx->h_pin[i];
     st->n_edges = edges;
@@ -1616,7 +1630,7 @@ int stage_begin(mgta_ctx *ctx, mgta_stage_stats *st, StageTimer &tm) {
 }
 int stage_end(mgta_ctx *ctx, mgta_stage_stats *st, StageTimer &tm) {
     CK(cudaEventRecord(tm.ev1, ctx->stream));
-    CK(cudaEventSynchronize(tm.ev1));
+    CK(mgta_stream_wait(ctx->stream));                               // ev1 is the last thing on the stream
     CK(cudaEventElapsedTime(&st->ms_total, tm.ev0, tm.ev1));
     cudaEventDestroy(tm.ev0);
     cudaEventDestroy(tm.ev1);
@@ -1654,7 +1668,7 @@ extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
     }
     if (edge_counting) {
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
     }
     return stage_end(ctx, st, tm);
@@ -1690,7 +1704,7 @@ extern "C" int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items) {
                                                                                               (unsigned)world, d_out);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctx->h_pin, d_out, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         uint64_t mx = 0;
         for (int d = 0; d < world; ++d) mx = std::max<uint64_t>(mx, ctx->h_pin[d]);
         ctx->slab_suggest = ((uint64_t)((double)mx / world * 1.02) + 4096 + 31) & ~(uint64_t)31;
@@ -1722,7 +1736,7 @@ extern "C" int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts, int
     st->n_edges = ctx->n_edges;
     if (edge_counting) {
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
     }
     if ((rc = stage_end(ctx, st, tm))) return rc;
@@ -1778,7 +1792,7 @@ extern "C" int mgta_get_is_solid(mgta_ctx *ctx, uint8_t *host, uint64_t n_bytes)
     }
     std::vector<uint32_t> h(words);
     CK(cudaMemcpyAsync(h.data(), tmp, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     cudaFree(tmp);
     memset(host, 0, n_bytes);
     memcpy(host, h.data(), std::min<uint64_t>(n_bytes, (bits + 7) / 8));
@@ -1804,7 +1818,7 @@ extern "C" int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_
                                                                                       ctx->opt.kmer_k, nk1, ctx->d_solid);
         CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     cudaFree(tmp);
     ctx->edges_valid = false;
     ctx->edges_all_valid = false;
@@ -1821,7 +1835,7 @@ extern "C" int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t
     if (host && take) {
         CK(cudaSetDevice(ctx->opt.device));
         CK(cudaMemcpyAsync(host, ctx->d_cand, take * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
     }
     return MGTA_OK;
 }
@@ -1847,7 +1861,7 @@ extern "C" int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t
     CK(cudaSetDevice(ctx->opt.device));
     const size_t row = (size_t)ctx->edge_row_words * 4;
     if (n_rows_total > ctx->edges_all_cap || !ctx->d_edges_all) {  // grows only: no allocation on the steady-state path
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(mgta_stream_wait(ctx->stream));
         cudaFree(ctx->d_edges_all);
         ctx->d_edges_all = nullptr; ctx->edges_all_cap = 0;
         const uint64_t ncap = n_rows_total + n_rows_total / 16 + 64;
@@ -1857,7 +1871,7 @@ extern "C" int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t
     if (ctx->n_edges)
         CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ctx->d_edges_all) + my_offset_rows * row, ctx->d_edges, ctx->n_edges * row,
                            cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
     ctx->n_edges_all = n_rows_total;
     ctx->edges_all_valid = true;
     *dev = ctx->d_edges_all;
