@@ -97,7 +97,7 @@ struct mgta_ctx {
     bool solid_valid = false;              // d_solid holds the is_solid vector of the last stage 1 (derived on demand)
     bool stage1_done = false;
     uint32_t *d_hist_s2 = nullptr;
-    int PB = 20;                           // prefix bits of a stage-2 tile: min(20 + log2(world), 24, 2(k-1)), >= 16
+    int PB = 19;                           // prefix bits of a stage-2 tile: min(19 + log2(world), 24, 2(k-1)), >= 16
     uint32_t *h_hist2 = nullptr;           // pinned copy of d_hist_s2
     uint64_t n_positions = 0;              // edge offsets over all reads
     bool n_positions_valid = false;
@@ -297,13 +297,16 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_totals, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ec, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ctr, CTR_COUNT * 4)) != cudaSuccess) return fail("cudaMalloc", e);
-    // stage-2 prefix tiles: 2^20 for one GPU; the item count grows with the shards (weak scaling), so each doubling of the
+    // stage-2 prefix tiles: 2^19 for one GPU; the item count grows with the shards (weak scaling), so each doubling of the
     // world adds a prefix bit and the tiles keep their size (measured at 8 GPUs with 2^20 tiles: every tile overflows
     // the on-chip window, MSD levels run for all of them and the sort slows from 67 to 96 ms).
     {
         int wb = 0;
         while ((1 << wb) < opts->world) ++wb;
-        ctx->PB = std::min(std::min(20 + wb, 24), 2 * (opts->kmer_k - 1));
+        // 2^19 tiles per shard: 512 level-1 bins (k_item_part writes runs twice as long as with 1024: 22.1 -> 14.7 ms at
+        // 20M x 150) and room below the 1024-bin batch limit for unevenly wide shard ranges; the few tiles that then exceed
+        // the on-chip window take the MSD levels (+3.5 ms)
+        ctx->PB = std::min(std::min(19 + wb, 24), 2 * (opts->kmer_k - 1));
         if (const char *e2 = getenv("MGTA_S2_PB")) ctx->PB = std::max(16, std::min(std::min(atoi(e2), 24), 2 * (opts->kmer_k - 1)));   // test hook
     }
     if ((e = cudaMalloc(&ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
