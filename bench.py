@@ -422,13 +422,22 @@ def main():
         if n2:
             kern.append(("s2.k_item_part", st2["ms_extract"], rows * row_bytes * max(1, st2["n_batches"]) + n2 * iw2 * 4))
             kern.append(("s2.k_split", st2["ms_partition"], 2 * n2 * iw2 * 4))
-            kern.append(("s2.k_chunk", st2["ms_sort_emit"], n2 * iw2 * 4 + st2["out_bytes"]))
+            kern.append(("s2.k_sort_emit", st2["ms_sort_emit"], n2 * iw2 * 4 + st2["out_bytes"]))
         kern.sort(key=lambda x: -x[1])
         top = kern[0]
         ach = top[2] / (top[1] / 1000.0) / 1e9 if top[1] > 0 else 0.0
         step_bytes = sum(k[2] for k in kern)
+        traffic = None                                 # DRAM bytes of one launch from the committed ncu capture, same configuration only
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_s8_traffic.json")))
+            c = tr["config"]
+            if (tr["kernel"] == top[0] and n_gpus == c["n_gpus"] and n_reads == c["reads"] and L == c["read_len"] and a.k == c["k"]
+                    and a.m == c["min_count"] and n2 == tr["items"]):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": pk_src, "algorithmic_bytes_per_launch": top[2],
+                    "traffic": traffic, "peak_source": pk_src, "algorithmic_bytes_per_launch": top[2],
                     "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_dev / 1000.0) / 1e9 / peak / n_gpus,
                     "kernels": [{"name": k[0], "ms": k[1], "bytes": k[2], "gbs": (k[2] / (k[1] / 1000.0) / 1e9 if k[1] > 0 else 0.0)}
                                 for k in kern]}

@@ -1172,9 +1172,19 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
     unsigned tab_cap = 4096;
     while (tab_cap > 256 && mercy_smem_bytes(W, tab_cap) > 200 * 1024) tab_cap >>= 1;
     const unsigned tab_limit = tab_cap - 600;
-    int bits = 2;
-    while (bits < 30 && (n_items_max >> bits) > tab_cap / 2) ++bits;
-    const unsigned lb2 = (unsigned)std::min(10, bits / 2), lb1 = (unsigned)bits - lb2, B1 = 1u << lb1;
+    // tiles of mean <= 0.6 * cap ITEMS: even if every item were a distinct S a 6-sigma tile stays below tab_limit; a tile
+    // that does not (ERR_TABLE_FULL) restarts the pass with one more partition bit
+    int bits = 2, lb2i = 0, lb1i = 0;
+    unsigned lb2 = 0, lb1 = 0, B1 = 0;
+    auto set_bits = [&](int extra) {
+        bits = 2;
+        while (bits < 30 && (n_items_max >> bits) > (uint64_t)tab_cap * 6 / 10) ++bits;
+        bits = std::min(30, bits + extra);
+        lb2i = std::min(10, bits / 2); lb1i = bits - lb2i;
+        lb2 = (unsigned)lb2i; lb1 = (unsigned)lb1i; B1 = 1u << lb1;
+    };
+    int bits_extra = 0;
+    set_bits(0);
     const unsigned T = split_chunk_items(IW);
     const int TP = IW <= 5 ? 2048 : 1024;
     const size_t budget = hbm_budget(ctx);
@@ -1284,6 +1294,11 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
                 unsigned long long mx = 0;
                 for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
                 slack = std::max(slack * 1.5, (double)mx / ((double)n_items_max / B1) * 1.05);
+                retry = true;
+                break;
+            }
+            if (dev_err == ERR_TABLE_FULL && bits_extra < 4) {    // a tile with more distinct (k-1)-mers than the table takes: finer tiles
+                set_bits(++bits_extra);
                 retry = true;
                 break;
             }
