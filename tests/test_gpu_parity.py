@@ -82,7 +82,7 @@ def test_gpu_small_sort_tiles_force_msd_levels(golden, read_lib):
     assert got["stats2"]["msd_levels"] >= 1
 
 
-@pytest.mark.parametrize("ds,k,m,budget", [("smoke", 31, 2, 24 << 20), ("adversarial", 27, 3, 24 << 20)])
+@pytest.mark.parametrize("ds,k,m,budget", [("smoke", 31, 2, 14 << 20), ("adversarial", 27, 3, 24 << 20)])
 def test_gpu_small_hbm_budget_forces_batches(read_lib, ds, k, m, budget):
     _, rd = read_lib(ds)
     got = run_gpu(rd, k, m, hbm_budget_bytes=budget)
