@@ -104,4 +104,36 @@ MGTA_HD void s1_mercy_item(const S1GroupMasks &g, bool solid, int head, int tail
     }
 }
 
+// ---- the per-read mercy scan (s2_read_mercy_prepare, s2.cpp:170-238) over position flags instead of sorted candidates.
+// bit(v, i): flag vector v at k-mer offset i of this read: 0 = a candidate with flag 1 ("no in"), 1 = a candidate with flag 2
+// ("no out"), 2 = any candidate ("has solid k-mer"), 3 = is_solid of edge offset i (asked only for i + k < L, and never
+// for an offset this scan has set).  set_solid(j): mark edge offset j.  Returns the number of edges marked ("Number mercy").
+template <class Bit, class SetSolid>
+MGTA_HD unsigned long long mercy_scan_read(int L, int k, Bit &&bit, SetSolid &&set_solid) {
+    if (L < k + 1) return 0;
+    int first_0_out = 1 << 30, last_0_in = -1;
+    bool any = false;
+    for (int i = 0; i + k <= L; ++i) {
+        if (bit(2, i)) any = true;
+        if (bit(1, i) && i < first_0_out) first_0_out = i;
+        if (bit(0, i)) last_0_in = i;
+    }
+    if (!any || last_0_in < first_0_out) return 0;                         // s2.cpp:203-205
+    unsigned long long added = 0;
+    int last_no_out = -1;
+    bool carry = false;                                                    // original is_solid[i - 1]: marks has_solid_kmer[i] too (s2.cpp:216-220)
+    for (int i = 0; i + k <= L; ++i) {
+        const bool sol = (i + k < L) && bit(3, i);                         // still the original value: this scan only sets offsets < i
+        const bool hs = bit(2, i) || sol || carry;
+        if (bit(0, i) && last_no_out != -1) {
+            for (int j = last_no_out; j < i; ++j) set_solid(j);
+            added += (unsigned long long)(i - last_no_out);
+        }
+        if (hs) last_no_out = -1;
+        if (bit(1, i)) last_no_out = i;
+        carry = sol;
+    }
+    return added;
+}
+
 }  // namespace mgta

@@ -316,36 +316,17 @@ __global__ void k_mercy_reads(const uint64_t *__restrict__ start, uint64_t n_sho
     if (r < n_short) {
         const uint64_t s0 = start[r];
         const int L = (int)(start[r + 1] - s0);
-        if (L >= k + 1) {
-            int first_0_out = 1 << 30, last_0_in = -1;
-            bool any = false;
-            for (int i = 0; i + k <= L; ++i) {
-                const uint64_t g = s0 + (uint64_t)i;
-                if (bit_at(touched, g)) any = true;
-                if (bit_at(no_out, g) && i < first_0_out) first_0_out = i;
-                if (bit_at(no_in, g)) last_0_in = i;
-            }
-            if (any && last_0_in >= first_0_out) {
-                int last_no_out = -1;
-                bool carry = false;                              // is_solid[i - 1]: marks has_solid_kmer[i] too (s2.cpp:216-220)
-                for (int i = 0; i + k <= L; ++i) {
-                    const uint64_t g = s0 + (uint64_t)i;
-                    const bool sol = (i + k < L) && bit_at(solid, g);      // read BEFORE this thread may set it below: bits
-                    // set by this scan lie strictly below i, and `carry` holds the original value of bit i - 1
-                    const bool hs = bit_at(touched, g) || sol || carry;
-                    if (bit_at(no_in, g) && last_no_out != -1) {
-                        for (int j = last_no_out; j < i; ++j) {
-                            const uint64_t e = s0 + (uint64_t)j;
-                            atomicOr(solid + (e >> 5), 1u << (e & 31));
-                        }
-                        added += (unsigned long long)(i - last_no_out);
-                    }
-                    if (hs) last_no_out = -1;
-                    if (bit_at(no_out, g)) last_no_out = i;
-                    carry = sol;
-                }
-            }
-        }
+        const volatile uint32_t *vsolid = solid;                   // written by this kernel: plain loads, not the read-only path
+        added = mercy_scan_read(L, k,
+                                [&](int v, int i) {
+                                    const uint64_t g = s0 + (uint64_t)i;
+                                    if (v == 3) return (bool)((vsolid[g >> 5] >> (g & 31)) & 1u);
+                                    return bit_at(v == 0 ? no_in : (v == 1 ? no_out : touched), g);
+                                },
+                                [&](int j) {
+                                    const uint64_t e = s0 + (uint64_t)j;
+                                    atomicOr(solid + (e >> 5), 1u << (e & 31));
+                                });
     }
     for (int o = 16; o; o >>= 1) added += __shfl_down_sync(0xFFFFFFFFu, added, o);
     if ((threadIdx.x & 31) == 0 && added) atomicAdd(num_mercy, added);

@@ -188,6 +188,37 @@ int logic_stage2(const uint32_t *seq, const uint64_t *start, int64_t n_reads, in
     return 0;
 }
 void logic_free(void *p) { free(p); }
+
+// The device's per-read mercy scan (cx1_emit.cuh mercy_scan_read, what k_mercy_bits + k_mercy_reads run) on the CPU:
+// candidates -> three flag vectors over base positions -> scan of every short read.  is_solid: the reference layout
+// ((max_len - k) * read + offset), updated in place.  Returns "Number mercy".
+int64_t logic_mercy(const uint64_t *start, int64_t n_short, int max_len, int k, const uint64_t *cands, int64_t n_cand,
+                    uint8_t *is_solid) {
+    const uint64_t total = start[n_short];
+    std::vector<uint8_t> v[3];
+    for (auto &x : v) x.assign(total + 1, 0);
+    for (int64_t i = 0; i < n_cand; ++i) {
+        const uint64_t pos = cands[i] >> 2;
+        const int flag = (int)(cands[i] & 3);
+        if (pos > total) return -1;
+        if (flag == 1) v[0][pos] = 1;
+        if (flag == 2) v[1][pos] = 1;
+        v[2][pos] = 1;
+    }
+    const int64_t nk1 = max_len - k;
+    int64_t num = 0;
+    for (int64_t r = 0; r < n_short; ++r) {
+        const uint64_t s0 = start[r];
+        const int L = (int)(start[r + 1] - s0);
+        num += (int64_t)mercy_scan_read(L, k,
+                                        [&](int w, int i) {
+                                            if (w == 3) { const int64_t b = nk1 * r + i; return (bool)((is_solid[b >> 3] >> (b & 7)) & 1); }
+                                            return (bool)v[w][s0 + (uint64_t)i];
+                                        },
+                                        [&](int j) { const int64_t b = nk1 * r + j; is_solid[b >> 3] |= (uint8_t)(1u << (b & 7)); });
+    }
+    return num;
+}
 }
 
 // ---- edge-centric path (v2): canonical (k+1)-mer multiset -> stage-1 outputs, and

@@ -134,3 +134,25 @@ def test_edge_centric_logic_matches_oracle(logic, read_lib, ds, k, m, mercy):
 def lib_stage1_edges(lib, rd, k, m, solid, ec):
     n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
     return lib.logic_stage1_edges(_p(rd["seq"]), _p(rd["start"]), n, ns, rd["max_len"], k, m, _p(solid), _p(ec))
+
+
+MERCY_SCAN_CASES = [("tiny", 25, 2), ("smoke", 31, 2), ("smoke", 27, 3), ("smoke", 41, 3), ("adversarial", 31, 2),
+                    ("adversarial", 27, 3), ("adversarial", 64, 2), ("xander", 29, 2), ("xander", 44, 2)]
+
+
+@pytest.mark.parametrize("ds,k,m", MERCY_SCAN_CASES)
+def test_device_mercy_scan_on_cpu_matches_oracle(logic, read_lib, ds, k, m):
+    """cx1_emit.cuh mercy_scan_read (the code k_mercy_reads runs) over position flag vectors vs the oracle's restatement of
+    s2_read_mercy_prepare over sorted candidates: same is_solid, same "Number mercy"."""
+    _, rd = read_lib(ds)
+    solid, _, cands = O.stage1(rd, k, m, True)
+    exp = solid.copy()
+    exp_n = O.mercy(rd, k, exp, cands)
+    got = solid.copy()
+    shuffled = np.random.default_rng(5).permutation(cands)          # the device list is unordered and may hold duplicates
+    shuffled = np.concatenate([shuffled, shuffled[: len(shuffled) // 3]]).astype(np.uint64)
+    logic.logic_mercy.restype = ctypes.c_int64
+    n = logic.logic_mercy(_p(np.ascontiguousarray(rd["start"], dtype=np.uint64)), ctypes.c_int64(rd["n_reads"]), rd["max_len"], k,
+                          _p(shuffled), ctypes.c_int64(len(shuffled)), _p(got))
+    assert n == exp_n
+    assert np.array_equal(got, exp)
