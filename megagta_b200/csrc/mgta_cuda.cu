@@ -185,11 +185,6 @@ struct Plan {
     uint64_t out_cap;
 };
 
-size_t chunk_smem_bytes(int IW, unsigned capi) {
-    return (size_t)IW * capi * 4 + CHUNK_WARPS * 256 * 2 + 256 * 4 + 2 * (capi / 32 + 2) * 4 + (CHUNK_WARPS + 2) * 4 +
-           2 * (size_t)capi * 2;
-}
-
 void make_plan(Plan &pl, int stage, int k, int cap_override) {
     pl.stage = stage;
     pl.k = k;
@@ -1344,7 +1339,7 @@ int ensure_solid(mgta_ctx *ctx) {
 
 // ---- the emission pipeline -------------------------------------------------------------------------
 // {(canonical edge, multiplicity)} -> stage-2 items (S a | flags, multiplicity) -> two key-prefix partition levels
-// (exact offsets) -> per-tile on-chip sort + W/last/tip/multiplicity records (k_chunk<2>) -> sink.
+// (exact offsets) -> per-window on-chip sort + W/last/tip/multiplicity records (k_sort_emit) -> sink.
 int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, mgta_stage_stats *st) {
     const int k = ctx->opt.kmer_k;
     const int WE = edge_words(k);
