@@ -260,6 +260,24 @@ def main():
     sharded_upload = world > 1 and not a.root_upload
     per_words = a.reads_per_gpu * L // 16                      # words of one shard's slice (reads_per_gpu * L % 16 == 0)
     assert not sharded_upload or (a.reads_per_gpu * L) % 16 == 0 and a.reads_per_gpu % 1_000_000 == 0
+    # Pinned staging buffers should live on the NUMA node the GPU hangs off (first touch follows the thread): bind this
+    # process to the GPU's CPUs (NVML) while it allocates and runs the GPU arm; the CPU baseline gets all cores back.
+    full_affinity = os.sched_getaffinity(0)
+    near_count = len(full_affinity)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 16)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & full_affinity
+        if len(near) >= 2:
+            os.sched_setaffinity(0, near)
+            near_count = len(near)
+    except Exception:
+        pass
     t0 = time.time()
     if sharded_upload:
         seq, start = synth.packed_metagenome(a.reads_per_gpu, L, seed=a.seed, first_read=rank * a.reads_per_gpu, n_genomes=n_genomes(a, world),
@@ -454,6 +472,10 @@ def main():
                              if ref_s2_items else None}
         # bytes the reference's LSD model would move per item vs what the kernels above move
         cpu_baseline = None
+        try:
+            os.sched_setaffinity(0, full_affinity)                 # the reference arm uses every host core
+        except Exception:
+            pass
         if n_gpus == 1 and not a.no_cpu_baseline:
             dt, e, kind, cores = time_reference(sample_prefix, a, work, "cpu")
             cpu_baseline = {"value": e / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
@@ -471,6 +493,7 @@ def main():
                                       else "scan-sharded: each shard scans 1/N of the reads, NCCL all-to-all of the items by hash owner"),
                            "upload": ("rank 0 H2D" + (" + NCCL broadcast" if world > 1 else "") if not sharded_upload
                                       else "every rank H2D of its slice + NCCL all-gather"),
+                           "cpu_affinity": "GPU-local CPUs (%d of %d) for the GPU arm" % (near_count, len(full_affinity)),
                            "gen_seconds": gen_s},
                 "e2e": {"value": edges / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
