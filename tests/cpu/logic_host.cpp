@@ -252,16 +252,48 @@ static void count_edges_t(const Reads &rd, const uint8_t *is_solid_filter, std::
 
 template <int W> struct Item2W { uint32_t key[W]; uint32_t mult; };
 
+static int64_t g_last_items = 0;      // stage-2 items the last logic_stage2_edges call generated (before the group logic)
+
+#include <set>
 template <int W, int WE>
-static void emit_edges_t(const Reads &rd, const std::map<EKey, std::pair<uint32_t, uint32_t>> &tab, bool apply_threshold, Out2 &out) {
+static void emit_edges_t(const Reads &rd, const std::map<EKey, std::pair<uint32_t, uint32_t>> &tab, bool apply_threshold, Out2 &out,
+                         bool node_filter = false) {
     const int k = rd.k;
     std::vector<Item2W<W>> items;
+    auto mult_of = [&](const std::pair<uint32_t, uint32_t> &c) {
+        return apply_threshold ? (c.first >= (uint32_t)rd.m ? c.first : c.second) : c.first;
+    };
+    // node filter: a $-item is dropped by output_() exactly when a solid edge enters (left $) /
+    // leaves (right $) the k-mer it hangs off, so it need not be generated then.  in_nodes / out_nodes: the k-mers some solid
+    // oriented edge ends in / starts from.
+    typedef std::array<uint32_t, W> NKey;
+    std::set<NKey> in_nodes, out_nodes;
+    auto node = [&](const uint32_t (&X)[W], int c) { uint32_t Y[W]; sub_chars<W>(X, c, k, Y); NKey n; for (int w = 0; w < W; ++w) n[w] = Y[w]; return n; };
+    if (node_filter)
+        for (auto &kv : tab) {
+            if (!mult_of(kv.second)) continue;
+            uint32_t E[W], R[W];
+            for (int w = 0; w < W; ++w) E[w] = w < WE ? kv.first[w] : 0u;
+            revcomp<W>(E, k + 1, R);
+            out_nodes.insert(node(E, 0)); in_nodes.insert(node(E, 1));
+            out_nodes.insert(node(R, 0)); in_nodes.insert(node(R, 1));
+        }
     for (auto &kv : tab) {
-        uint32_t mult = apply_threshold ? (kv.second.first >= (uint32_t)rd.m ? kv.second.first : kv.second.second) : kv.second.first;
+        uint32_t mult = mult_of(kv.second);
         if (!mult) continue;
-        uint32_t key[WE]; for (int w = 0; w < WE; ++w) key[w] = kv.first[w];
-        s2_items_of_edge<W, WE>(key, k, [&](const uint32_t(&y)[W]) { Item2W<W> it; memcpy(it.key, y, sizeof(it.key)); it.mult = mult; items.push_back(it); });
+        auto put = [&](const uint32_t(&y)[W]) { Item2W<W> it; memcpy(it.key, y, sizeof(it.key)); it.mult = mult; items.push_back(it); };
+        if (node_filter) {
+            uint32_t E[W], R[W];
+            for (int w = 0; w < W; ++w) E[w] = w < WE ? kv.first[w] : 0u;
+            revcomp<W>(E, k + 1, R);
+            const bool left = !in_nodes.count(node(E, 0)), right = !out_nodes.count(node(E, 1));
+            s2_edge_items<W>(E, R, cmp_words<W>(E, R) == 0, left, right, k, put);
+        } else {
+            uint32_t key[WE]; for (int w = 0; w < WE; ++w) key[w] = kv.first[w];
+            s2_items_of_edge<W, WE>(key, k, put);
+        }
     }
+    g_last_items = (int64_t)items.size();
     std::sort(items.begin(), items.end(), [](const Item2W<W> &a, const Item2W<W> &b) {
         for (int i = 0; i < W; ++i) if (a.key[i] != b.key[i]) return a.key[i] < b.key[i];
         return false;
@@ -331,12 +363,13 @@ int logic_stage2_edges(const uint32_t *seq, const uint64_t *start, int64_t n_rea
     memset(meta, 0, 65536 * 3 * 8); memset(totals, 0, 10 * 8);
     std::map<EKey, std::pair<uint32_t, uint32_t>> tab;
     static uint8_t dummy[8];
-    DISPATCH(edge_words(k), (count_edges_t<WW>(rd, fused ? nullptr : (is_solid ? is_solid : dummy), tab, nullptr)));
+    DISPATCH(edge_words(k), (count_edges_t<WW>(rd, (fused & 1) ? nullptr : (is_solid ? is_solid : dummy), tab, nullptr)));
     const int WE = edge_words(k);
-    DISPATCH2(key_words_s2(k), WE, (emit_edges_t<W2, WEE>(rd, tab, fused != 0, out)));
+    DISPATCH2(key_words_s2(k), WE, (emit_edges_t<W2, WEE>(rd, tab, (fused & 1) != 0, out, (fused & 2) != 0)));
     *stream = (uint8_t *)malloc(out.bytes.size() + 8);
     memcpy(*stream, out.bytes.data(), out.bytes.size());
     *stream_bytes = (int64_t)out.bytes.size();
     return 0;
 }
+int64_t logic_last_items(void) { return g_last_items; }
 }

@@ -156,3 +156,25 @@ def test_device_mercy_scan_on_cpu_matches_oracle(logic, read_lib, ds, k, m):
                           _p(shuffled), ctypes.c_int64(len(shuffled)), _p(got))
     assert n == exp_n
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("ds,k,m,mercy", EDGE_CASES)
+def test_node_filter_drops_only_items_the_group_logic_drops(logic, read_lib, ds, k, m, mercy):
+    """Design check for the next step: with a k-mer node table (which k-mers a solid edge enters /
+    leaves) the $-items that output_() would drop anyway are never generated; the records must not change."""
+    _, rd = read_lib(ds)
+    exp_solid = None
+    if m > 1:
+        exp_solid, _, cands = O.stage1(rd, k, m, mercy)
+        if mercy:
+            O.mercy(rd, k, exp_solid, cands)
+    exp = O.stage2(rd, k, m, exp_solid)
+    logic.logic_last_items.restype = ctypes.c_int64
+    run_edges(logic, rd, k, m, exp_solid, fused=0)
+    n_all = logic.logic_last_items()
+    stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=2)
+    n_filtered = logic.logic_last_items()
+    assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
+    assert n_filtered <= n_all
+    if ds == "smoke" and k == 31 and m == 2 and not mercy:
+        assert n_filtered < 0.5 * n_all                  # two thirds of the items are $-items, almost all of them covered
