@@ -1087,7 +1087,6 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
         chunk_pref[s + 1] = chunk_pref[s] + (unsigned)((recv_counts[s] + cp.T - 1) / cp.T);
     }
     unsigned long long *d_xs = ctx->d_xs;                          // [in_start | in_count | chunk_pref]: 3 small arrays
-    auto free_xs = [&]() {};
     cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -1097,17 +1096,17 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
         bool retry = false;
         const uint64_t giants0 = st->n_giants;
         st->n_items = 0; st->n_batches = 0;
-        if ((rc = count_reset_outputs(ctx, cp))) { free_xs(); return rc; }
+        if ((rc = count_reset_outputs(ctx, cp))) return rc;
         CountLay L;
         unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
         count_layout(cp, L, n_batches, slack, X.xbytes, X.xbytes, (uint64_t)world * X.slab_items);
-        if (L.R != X.recv_off) { free_xs(); FAIL(MGTA_ERR_INTERNAL, "stage1_count: receive buffer moved"); }
-        if (L.total > budget) { free_xs(); FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the level-1 slabs (%zu B)", budget, L.total); }
-        if ((rc = ensure_arena_keep(ctx, L.total, X.recv_off + X.xbytes))) { free_xs(); return rc; }
+        if (L.R != X.recv_off) { FAIL(MGTA_ERR_INTERNAL, "stage1_count: receive buffer moved"); }
+        if (L.total > budget) { FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the level-1 slabs (%zu B)", budget, L.total); }
+        if ((rc = ensure_arena_keep(ctx, L.total, X.recv_off + X.xbytes))) return rc;
         for (unsigned batch = 0; batch < n_batches; ++batch) {
             const unsigned b_lo = cp.r_lo + batch * L.bins, b_hi = std::min(cp.r_hi, b_lo + L.bins);
             if (b_lo >= b_hi) break;
-            if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) { free_xs(); return rc; }
+            if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) return rc;
             SplitParams XP;
             memset(&XP, 0, sizeof(XP));
             XP.src = reinterpret_cast<uint32_t *>(ctx->arena + L.R); XP.dst = reinterpret_cast<uint32_t *>(ctx->arena + L.A);
@@ -1117,15 +1116,15 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
             XP.B1 = (unsigned)world; XP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
             XP.ticket = ctx->d_ctr + CTR_NLIST0; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
             XP.b_lo = b_lo; XP.b_hi = b_hi; XP.slab_cap = L.slab_cap; XP.hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
-            if ((rc = begin_timed(ctx, PH_PARTITION))) { free_xs(); return rc; }
-            if ((rc = launch_split(ctx, XP))) { free_xs(); return rc; }
-            if ((rc = end_timed(ctx))) { free_xs(); return rc; }
+            if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
+            if ((rc = launch_split(ctx, XP))) return rc;
+            if ((rc = end_timed(ctx))) return rc;
             st->n_launches++;
             bool overflow = false;
             double need = slack;
-            if ((rc = count_batch_tail(ctx, cp, L, b_lo, b_hi, n_batches, batch, slack, st, overflow, need))) { free_xs(); return rc; }
+            if ((rc = count_batch_tail(ctx, cp, L, b_lo, b_hi, n_batches, batch, slack, st, overflow, need))) return rc;
             if (overflow) {
-                if (attempt >= 6) { free_xs(); FAIL(MGTA_ERR_MEM, "level-1 hash bins overflow their slabs even with %.1fx slack", slack); }
+                if (attempt >= 6) { FAIL(MGTA_ERR_MEM, "level-1 hash bins overflow their slabs even with %.1fx slack", slack); }
                 slack = need;
                 st->n_giants = giants0 + 1;
                 retry = true;
@@ -1134,7 +1133,6 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
         }
         if (!retry) break;
     }
-    free_xs();
     ctx->edges_valid = true;
     return MGTA_OK;
 }
