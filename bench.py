@@ -467,6 +467,8 @@ def main():
             P = -(-(bits - 16) // 8)
             return (4 * W + (8 if stage == 1 else 0)) * (2 + 2 * P)
         ref_i1 = n_reads * (L - a.k + 4) if a.m > 1 else 0
+        # SURVEY 8(d)'s named counter: DRAM bytes the sort kernel moves per SdBG edge (from the same ncu capture)
+        roofline["sort_bytes_per_edge"] = traffic / edges if traffic and edges else None
         roofline["model"] = {"s1_items_ref": ref_i1, "s2_items_ref": ref_s2_items, "bytes_per_item": [model_bytes_per_item(1), model_bytes_per_item(2)],
                              "frac": ((ref_i1 * model_bytes_per_item(1) + ref_s2_items * model_bytes_per_item(2)) / (ms_dev / 1000.0) / 1e9 / peak / n_gpus)
                              if ref_s2_items else None}
