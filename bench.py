@@ -44,19 +44,39 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--genomes-per-gpu", type=int, default=64)
+    ap.add_argument("--total-reads", type=int, default=0,
+                    help="strong scaling: this many reads in all, split over the GPUs (0 = weak scaling with --reads-per-gpu each)")
+    ap.add_argument("--genomes", type=int, default=0, help="genomes of the community (0 = --genomes-per-gpu x GPUs; strong scaling: x total/20M)")
+    ap.add_argument("--no-hash", action="store_true", help="skip the (untimed) parity hashes of the GPU output")
+    ap.add_argument("--full-reference", action="store_true",
+                    help="N=1: also build the WHOLE workload with the reference on the host cores (untimed) and compare the hashes")
     ap.add_argument("--phases", action="store_true", help="diagnostic: per-phase host wall times of every rank on stderr (adds syncs)")
     ap.add_argument("--root-upload", action="store_true",
                     help="N>1: rank 0 uploads all reads and broadcasts them (default: every rank uploads its slice, NCCL all-gather)")
     ap.add_argument("--replicated-scan", action="store_true",
                     help="N>1: every shard scans ALL reads for its hash range (no item all-to-all); default is the scan-sharded stage 1")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.total_reads:
+        assert a.total_reads % (a.gpus * 1_000_000) == 0, "--total-reads must be a multiple of 1M x GPUs"
+        a.reads_per_gpu = a.total_reads // a.gpus
+    return a
 
 
 def n_genomes(a, n_gpus):
     """Weak scaling keeps the per-GPU work fixed: the community grows with the read set (64 genomes per 20M reads, the
     density of BASELINE.json configs[1]), so coverage and the SdBG edges per read stay those of the 1-GPU workload.  With a
     fixed community the edge count saturates as reads are added and edges/s would fall for reasons unrelated to the code."""
+    if a.genomes:
+        return a.genomes
+    if a.total_reads:                                   # strong scaling: the community of the whole read set, whatever N
+        return a.genomes_per_gpu * max(1, a.total_reads // 20_000_000)
     return a.genomes_per_gpu * n_gpus
+
+
+def sample_genomes(a):
+    """The CPU sample is drawn from the SAME community at every N (the N = 1 workload's when scaling weakly), so the
+    reference arm's value does not wander with N."""
+    return a.genomes or (n_genomes(a, 1))
 
 
 def workload_name(a, n_gpus):
@@ -64,24 +84,44 @@ def workload_name(a, n_gpus):
         a.reads_per_gpu * n_gpus // 1_000_000, a.read_len, a.k, a.m)
 
 
+def bucket_xsum(stream, meta, wpt):
+    """Composable checksum of a shard's record stream: sum over its non-empty lv1 buckets of a keyed 64-bit digest of the
+    bucket's bytes (mod 2^64).  Buckets are disjoint between shards and batches, so the sums of N shards add up to the
+    1-GPU value; equal sums <=> equal per-bucket byte strings (up to digest collisions)."""
+    import hashlib
+    m = np.asarray(meta, dtype=np.int64)
+    sizes = m[:, 0] * 2 + m[:, 2] * 2 + m[:, 1] * 4 * wpt
+    off, acc = 0, 0
+    mv = memoryview(stream)
+    for b in np.nonzero(sizes)[0]:
+        n = int(sizes[b])
+        acc += int.from_bytes(hashlib.blake2b(mv[off:off + n], digest_size=8, salt=int(b).to_bytes(8, "little")).digest(), "little")
+        off += n
+    assert off == len(stream), "per-bucket table does not add up to the stream"
+    return acc & 0xFFFFFFFFFFFFFFFF
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def auto_sample(a):
+    """Reads of the bounded CPU sample: as many as keep 25 reference runs within the arm's time budget
+    (measured: ~5 s per 1M x 150 bp reads on 16 cores, ~3 s on 32)."""
     if a.sample_reads:
         return a.sample_reads
     cores = os.cpu_count() or 1
-    return min(a.reads_per_gpu, 1_000_000 if cores <= 16 else 2_000_000)
+    return min(a.reads_per_gpu, 2_000_000 if cores <= 16 else 4_000_000)
 
 
 def write_sample(a, work):
     from megagta_b200 import synth
     n = auto_sample(a)
     prefix = os.path.join(work, "sample")
-    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n, n_genomes=n_genomes(a, a.gpus))
+    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n, n_genomes=sample_genomes(a))
     return prefix, n
 
 
-def time_reference(prefix, a, work, tag):
-    """One run of the unmodified reference buildgraph (oracle/_ref) on all host cores -> (seconds, edges, kind)."""
+def time_reference(prefix, a, work, tag, want_hash=False):
+    """One run of the unmodified reference buildgraph (oracle/_ref) on all host cores
+    -> (seconds, edges, kind, cores, hashes or None)."""
     from oracle import oracle as O
     from megagta_b200 import sdbg_io
     cores = os.cpu_count() or 2
@@ -90,15 +130,28 @@ def time_reference(prefix, a, work, tag):
         t = time.time()
         O.run_ref_buildgraph(prefix, out, a.k, a.m, threads=max(2, cores))
         dt = time.time() - t
-        hdr, _ = sdbg_io.read_info(out)
+        hashes = None
+        if want_hash:
+            hdr, stream, meta = sdbg_io.canonical(out)
+            hashes = {"stream_hash": sdbg_io.stream_hash(stream), "meta_hash": sdbg_io.meta_hash(meta), "stream_bytes": len(stream),
+                      "xsum": "%016x" % bucket_xsum(stream, meta, hdr["words_per_tip_label"])}
+            del stream
+        else:
+            hdr, _ = sdbg_io.read_info(out)
         for f in os.listdir(work):
             if f.startswith("ref_" + tag):
                 os.remove(os.path.join(work, f))
-        return dt, hdr["total_size"], "reference", max(2, cores)
+        return dt, hdr["total_size"], "reference", max(2, cores), hashes
     rd = O.load_read_lib(prefix)                      # fall back to the single-threaded C restatement
     t = time.time()
     res = O.build_graph(rd, a.k, a.m)
-    return time.time() - t, int(res["meta"][:, 0].sum()), "port", 1
+    dt = time.time() - t
+    hashes = None
+    if want_hash:
+        wpt = (2 * a.k + 31) // 32
+        hashes = {"stream_hash": sdbg_io.stream_hash(res["stream"]), "meta_hash": sdbg_io.meta_hash(res["meta"]),
+                  "stream_bytes": len(res["stream"]), "xsum": "%016x" % bucket_xsum(res["stream"], res["meta"], wpt)}
+    return dt, int(res["meta"][:, 0].sum()), "port", 1, hashes
 
 
 def run_reference_arm(a):
@@ -107,19 +160,21 @@ def run_reference_arm(a):
         return
     work = tempfile.mkdtemp(prefix="mgta_bench_ref_")
     prefix, n = write_sample(a, work)
-    times, edges, kind, cores = [], 0, "reference", 1
+    times, edges, kind, cores, hashes = [], 0, "reference", 1, None
     for i in range(a.warmup + a.steps):
-        dt, edges, kind, cores = time_reference(prefix, a, work, str(i))
+        dt, edges, kind, cores, h = time_reference(prefix, a, work, str(i), want_hash=(i == 0))
+        hashes = hashes or h
         if i >= a.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
     value = edges / (ms / 1000.0)
-    sample = "first %d reads of the workload (%d x %d bp), whole buildgraph, %d threads" % (n, n, a.read_len, cores)
+    sample = "first %d reads of the %d-genome community (%d x %d bp), whole buildgraph, %d threads" % (n, sample_genomes(a), n, a.read_len, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(a, a.gpus), "genomes": n_genomes(a, a.gpus), "sample": sample, "edges_per_step": edges},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if a.total_reads else "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "reads_per_s": n / (ms / 1000.0),
+            "config": {"workload": workload_name(a, a.gpus), "genomes": n_genomes(a, a.gpus), "sample": sample, "sample_reads": n,
+                       "edges_per_step": edges, "sample_hashes": hashes},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "reads_per_s": n / (ms / 1000.0)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -287,7 +342,8 @@ def main():
         start_pin = torch.from_numpy((start[:a.reads_per_gpu] + np.uint64(rank * a.reads_per_gpu * L)).view(np.int64)).pin_memory()
         del seq, start
     elif rank == 0:
-        seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix, bin_reads=sample_n, n_genomes=n_genomes(a, world))
+        seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix,
+                                             bin_reads=n_reads if (a.full_reference and world == 1) else sample_n, n_genomes=n_genomes(a, world))
         seq_pin = torch.from_numpy(seq).pin_memory()
         start_pin = torch.from_numpy(start.view(np.int64)).pin_memory()
         del seq, start
@@ -397,6 +453,26 @@ def main():
             sampler.stop_flag = True
             sampler.join()
 
+    # ---- parity evidence, outside every timed region: hashes of the records the last step's graph emits
+    parity = {}
+    wpt = (2 * a.k + 31) // 32
+    if not a.no_hash:
+        with torch.cuda.stream(stream):
+            h_stream, h_meta, h_totals = ctx.stage2(collect=True)
+        xs = bucket_xsum(h_stream, h_meta, wpt)
+        part = torch.tensor([xs & 0xFFFFFFFF, xs >> 32, len(h_stream), int(h_meta[:, 0].sum()), int(h_meta[:, 1].sum())], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        pl = [int(x) for x in part.tolist()]
+        parity = {"xsum": "%016x" % ((pl[0] + (pl[1] << 32)) & 0xFFFFFFFFFFFFFFFF), "stream_bytes": pl[2], "total_size": pl[3],
+                  "num_tips": pl[4],
+                  "xsum_def": "sum over lv1 buckets of blake2b-64(bucket bytes, salt = bucket) mod 2^64: composable over shards"}
+        if world == 1:
+            from megagta_b200 import sdbg_io
+            parity["stream_hash"] = sdbg_io.stream_hash(h_stream)
+            parity["meta_hash"] = sdbg_io.meta_hash(h_meta)
+        del h_stream
+
     def total(x):
         t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
         if world > 1:
@@ -479,13 +555,42 @@ def main():
         except Exception:
             pass
         if n_gpus == 1 and not a.no_cpu_baseline:
-            dt, e, kind, cores = time_reference(sample_prefix, a, work, "cpu")
-            cpu_baseline = {"value": e / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,
+            if a.full_reference:                                   # the sample library is the first sample_n records of the full one
+                full_prefix = os.path.join(work, "full")
+                os.rename(sample_prefix + ".bin", full_prefix + ".bin")
+                with open(full_prefix + ".lib_info", "w") as f:
+                    f.write("%d %d\nsynthetic\n0 %d %d se\n" % (n_reads * L, n_reads, n_reads - 1, L))
+                rec = 4 * (1 + (L + 15) // 16)
+                with open(full_prefix + ".bin", "rb") as fi, open(sample_prefix + ".bin", "wb") as fo:
+                    fo.write(fi.read(sample_n * rec))
+                with open(sample_prefix + ".lib_info", "w") as f:
+                    f.write("%d %d\nsynthetic\n0 %d %d se\n" % (sample_n * L, sample_n, sample_n - 1, L))
+            dt, e, kind, cores, ref_h = time_reference(sample_prefix, a, work, "cpu", want_hash=not a.no_hash)
+            cpu_baseline = {"value": e / dt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt, "reads_per_s": sample_n / dt,
                             "sample": "first %d reads of the workload (%d x %d bp), whole buildgraph" % (sample_n, sample_n, L)}
+            if not a.no_hash:
+                # the GPU path on the SAME sample the reference just built: hashes must agree (cx1_read2sdbg_s2.cpp:742-835 output)
+                from megagta_b200 import sdbg_io
+                ws = (sample_n * L + 15) // 16
+                with torch.cuda.stream(stream), cabi.Context(a.k, a.m, device=local, stream=stream.cuda_stream) as c2:
+                    c2.set_reads(seq_pin.numpy().view(np.uint32)[:ws], start_pin.numpy().view(np.uint64)[:sample_n + 1], max_len=L)
+                    if a.m > 1:
+                        c2.stage1()
+                    s2_stream, s2_meta, _ = c2.stage2()
+                got = {"stream_hash": sdbg_io.stream_hash(s2_stream), "meta_hash": sdbg_io.meta_hash(s2_meta), "stream_bytes": len(s2_stream),
+                       "xsum": "%016x" % bucket_xsum(s2_stream, s2_meta, wpt)}
+                parity["sample"] = {"reads": sample_n, "gpu": got, "reference": ref_h, "ok": got == ref_h}
+                del s2_stream
+            if a.full_reference:
+                dtf, ef, kindf, coresf, full_h = time_reference(full_prefix, a, work, "full", want_hash=True)
+                mine = {k: parity.get(k) for k in ("stream_hash", "meta_hash", "stream_bytes", "xsum")}
+                parity["full"] = {"reads": n_reads, "gpu": mine, "reference": full_h, "ok": mine == full_h, "reference_seconds": dtf,
+                                  "reference_cores": coresf, "reference_edges_per_s": ef / dtf, "reference_reads_per_s": n_reads / dtf}
         line = {"metric": METRIC, "value": edges / (ms_dev / 1000.0), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u32", "data": "synthetic",
+                "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if a.total_reads else "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "reads_per_s": n_reads / (ms_dev / 1000.0),
                 "config": {"workload": workload_name(a, n_gpus), "reads": n_reads, "read_len": L, "k": a.k, "min_count": a.m,
+                           "parity": parity,
                            "genomes": n_genomes(a, n_gpus),
                            "edges_per_step": edges, "s1_items": total_items(st1, world, dist, dev, torch),
                            "s2_items": total_items(st2, world, dist, dev, torch),

@@ -115,13 +115,65 @@ MGTA_HD void canonical_edge(const uint32_t *words, uint32_t q, int k, uint32_t (
 // all stage-2 items of a canonical edge (both orientations, $-items unconditionally: the emission
 // rules s2.cpp:801-818 drop a $-item whenever a real edge covers it, which is exactly the case in
 // which the reference would not have produced it at every occurrence).  W = key_words_s2(k) >= WE.
+// tips = false: only the (up to two) real items b S a -- the node pass below supplies the $-items that survive.
 template <int W, int WE, class Emit>
-MGTA_HD void s2_items_of_edge(const uint32_t (&key)[WE], int k, Emit &&emit) {
+MGTA_HD void s2_items_of_edge(const uint32_t (&key)[WE], int k, Emit &&emit, bool tips = true) {
     uint32_t E[W], R[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) E[w] = w < WE ? key[w < WE ? w : 0] : 0u;
     revcomp<W>(E, k + 1, R);
-    s2_edge_items<W>(E, R, cmp_words<W>(E, R) == 0, true, true, k, emit);
+    s2_edge_items<W>(E, R, cmp_words<W>(E, R) == 0, tips, tips, k, emit);
+}
+
+// ---- node pass.  output_() (s2.cpp:801-818) drops a $-item whenever a real edge covers it, so the
+// only $-items that reach the records are those of TIP k-mers: oriented k-mers X with solid edges leaving but none
+// entering (left tip: item ($, X)) or entering but none leaving (right tip: item (X, $)), with multiplicity = the summed
+// multiplicities of the edges on the other side.  Both are functions of two weights per CANONICAL k-mer c:
+//     out(c) = sum of mult over oriented solid edges that start with c,   in(c) = ... that end in c,
+// and by reverse-complement symmetry out(rc c) = in(c), in(rc c) = out(c).  A canonical edge E contributes to the
+// canonical forms of its first and last k-mer (its reverse complement contributes the same again, so it is not visited;
+// a palindromic edge starts with X and ends in rc X, one and the same contribution).
+MGTA_HD int kmer_words(int k) { return (2 * k + 31) / 32; }
+
+// emit(c[WE], dir): canonical k-mer zero padded to WE words (the first kmer_words(k) hold it), dir 0: out(c) += mult,
+// dir 1: in(c) += mult.  A palindromic k-mer (k even) gets both kinds on one entry; its in and out are equal by
+// symmetry, so it is never a tip (s2_tip_items is not called for it).
+template <int WE, class Emit>
+MGTA_HD void node_ops_of_edge(const uint32_t (&E)[WE], int k, Emit &&emit) {
+    uint32_t R[WE], X[WE], XR[WE];
+    revcomp<WE>(E, k + 1, R);
+    const bool pal = cmp_words<WE>(E, R) == 0;
+    sub_chars<WE>(E, 0, k, X);                          // first k-mer; its reverse complement is the last k-mer of R
+    sub_chars<WE>(R, 1, k, XR);
+    {
+        const bool fw = cmp_words<WE>(X, XR) <= 0;
+        if (fw) emit(X, 0); else emit(XR, 1);
+    }
+    if (!pal) {
+        sub_chars<WE>(E, 1, k, X);                      // last k-mer; reverse complement = first k-mer of R
+        sub_chars<WE>(R, 0, k, XR);
+        const bool fw = cmp_words<WE>(X, XR) <= 0;
+        if (fw) emit(X, 1); else emit(XR, 0);
+    }
+}
+
+// The two stage-2 items of a tip k-mer C (zero padded to W = key_words_s2(k) words, RC its reverse complement, C != RC).
+// no_in: nothing enters C (so nothing leaves RC): C is a left tip, RC a right tip; else the other way round.
+//   left tip  L: ($, S = L[0..k-2], a = L[k-1])   key = L | (a != $) << 3 | $
+//   right tip T: (b = T[0], S = T[1..k-1], a = $)  key = T[1..k-1] | b
+template <int W, class Emit>
+MGTA_HD void s2_tip_items(const uint32_t (&C)[W], const uint32_t (&RC)[W], bool no_in, int k, Emit &&emit) {
+    uint32_t Y[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) Y[w] = no_in ? C[w] : RC[w];
+    Y[W - 1] |= (uint32_t)((1 << 3) | SENT);
+    emit(Y);
+    uint32_t T[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) T[w] = no_in ? RC[w] : C[w];
+    sub_chars<W>(T, 1, k - 1, Y);
+    Y[W - 1] |= (T[0] >> 30) & 3u;
+    emit(Y);
 }
 
 }  // namespace mgta

@@ -467,6 +467,7 @@ struct CountParams {
     unsigned long long edges_cap;
     uint32_t *hist_s2;                // histogram of the stage-2 items of the emitted edges by key prefix
     int s2_shift;
+    int real_only;                    // count only the real items b S a: the node pass adds the $-items of the tip k-mers
     unsigned *ovf_list, *n_ovf, ovf_cap;
     unsigned *err;
 };
@@ -688,7 +689,8 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
 #pragma unroll
                     for (int w = 0; w < WE; ++w) row[w] = key[w];
                     row[WE] = mult;
-                    s2_items_of_edge<W2, WE>(key, P.k, [&](const uint32_t(&y)[W2]) { atomicAdd(P.hist_s2 + (y[0] >> P.s2_shift), 1u); });
+                    s2_items_of_edge<W2, WE>(key, P.k, [&](const uint32_t(&y)[W2]) { atomicAdd(P.hist_s2 + (y[0] >> P.s2_shift), 1u); },
+                                             !P.real_only);
                 }
             }
             __syncthreads();
@@ -715,21 +717,23 @@ struct ItemPartParams {
     unsigned *err;
 };
 
-constexpr int ITEM_EDGES = 512;       // edges per CTA -> <= 3072 item slots
+constexpr int ITEM_SLOTS = 3072;      // item slots per CTA: 512 edges x 6 items, or 1536 edges x 2 real items
 
-template <int WE, bool PLUS>
+// PER = 6: all stage-2 items of an edge ($-items unconditionally; the group logic drops the covered ones);
+// PER = 2: the real items only -- the $-items of the tip k-mers come from the node pass (k_row_part)
+template <int WE, bool PLUS, int PER>
 __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W2 = PLUS ? WE + 1 : WE;
-    constexpr int IW = W2 + 1, SLOTS = ITEM_EDGES * 6;
+    constexpr int IW = W2 + 1, SLOTS = ITEM_SLOTS, EDGES = ITEM_SLOTS / PER;
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, SLOTS);
     const int tid = threadIdx.x;
     for (int i = tid; i < (int)P.NB; i += PART_THREADS) S.cnt[i] = 0;
     for (int i = tid; i < SLOTS; i += PART_THREADS) S.bin[i] = 0xFFFFu;
     __syncthreads();
-    const unsigned long long e0 = (unsigned long long)blockIdx.x * ITEM_EDGES;
-    for (int el = tid; el < ITEM_EDGES; el += PART_THREADS) {
+    const unsigned long long e0 = (unsigned long long)blockIdx.x * EDGES;
+    for (int el = tid; el < EDGES; el += PART_THREADS) {
         const unsigned long long e = e0 + el;
         if (e >= P.n_edges) break;
         const uint32_t *row = P.edges + e * (WE + 1);
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams
         s2_items_of_edge<W2, WE>(key, P.k, [&](const uint32_t(&y)[W2]) {
             const unsigned bkt = y[0] >> 16;
             if (bkt >= P.bkt_lo && bkt < P.bkt_hi) {
-                const int slot = el * 6 + j;
+                const int slot = el * PER + j;
                 const unsigned b = (y[0] >> P.sh1) - P.b1_lo;
 #pragma unroll
                 for (int w = 0; w < W2; ++w) S.stage[w * SLOTS + slot] = y[w];
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams
                 S.rank[slot] = (uint16_t)atomicAdd(&S.cnt[b], 1u);
             }
             ++j;
-        });
+        }, PER == 6);
     }
     __syncthreads();
     bin_scatter(S, SLOTS, IW, SLOTS, (int)P.NB, P.cursor1, P.dst, P.cap, 0ull, P.err);

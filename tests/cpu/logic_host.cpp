@@ -257,7 +257,7 @@ static int64_t g_last_items = 0;      // stage-2 items the last logic_stage2_edg
 #include <set>
 template <int W, int WE>
 static void emit_edges_t(const Reads &rd, const std::map<EKey, std::pair<uint32_t, uint32_t>> &tab, bool apply_threshold, Out2 &out,
-                         bool node_filter = false) {
+                         bool node_filter = false, bool node_pass = false) {
     const int k = rd.k;
     std::vector<Item2W<W>> items;
     auto mult_of = [&](const std::pair<uint32_t, uint32_t> &c) {
@@ -278,7 +278,38 @@ static void emit_edges_t(const Reads &rd, const std::map<EKey, std::pair<uint32_
             out_nodes.insert(node(E, 0)); in_nodes.insert(node(E, 1));
             out_nodes.insert(node(R, 0)); in_nodes.insert(node(R, 1));
         }
+    // node pass (the product's formulation): out / in weights per canonical k-mer from
+    // node_ops_of_edge, the $-items of the tip k-mers from s2_tip_items, real items only from the edges
+    if (node_pass) {
+        std::map<NKey, std::pair<uint64_t, uint64_t>> nodes;          // canonical k-mer -> (out, in)
+        for (auto &kv : tab) {
+            const uint32_t mult = mult_of(kv.second);
+            if (!mult) continue;
+            uint32_t E[WE];
+            for (int w = 0; w < WE; ++w) E[w] = kv.first[w];
+            node_ops_of_edge<WE>(E, k, [&](const uint32_t(&c)[WE], int dir) {
+                NKey n; n.fill(0);
+                for (int w = 0; w < kmer_words(k); ++w) n[w] = c[w];
+                auto &acc = nodes[n];
+                (dir ? acc.second : acc.first) += std::min<uint32_t>(mult, 65535u);
+            });
+            auto put = [&](const uint32_t(&y)[W]) { Item2W<W> it; memcpy(it.key, y, sizeof(it.key)); it.mult = mult; items.push_back(it); };
+            uint32_t key[WE]; for (int w = 0; w < WE; ++w) key[w] = kv.first[w];
+            s2_items_of_edge<W, WE>(key, k, put, false);
+        }
+        for (auto &kv : nodes) {
+            const uint64_t o = kv.second.first, i = kv.second.second;
+            uint32_t C[W], RC[W];
+            for (int w = 0; w < W; ++w) C[w] = kv.first[w];
+            revcomp<W>(C, k, RC);
+            if (cmp_words<W>(C, RC) == 0) continue;
+            if ((o == 0) == (i == 0)) continue;
+            const uint32_t wgt = (uint32_t)std::min<uint64_t>(o + i, 65535u);
+            s2_tip_items<W>(C, RC, i == 0, k, [&](const uint32_t(&y)[W]) { Item2W<W> it; memcpy(it.key, y, sizeof(it.key)); it.mult = wgt; items.push_back(it); });
+        }
+    }
     for (auto &kv : tab) {
+        if (node_pass) break;
         uint32_t mult = mult_of(kv.second);
         if (!mult) continue;
         auto put = [&](const uint32_t(&y)[W]) { Item2W<W> it; memcpy(it.key, y, sizeof(it.key)); it.mult = mult; items.push_back(it); };
@@ -365,7 +396,7 @@ int logic_stage2_edges(const uint32_t *seq, const uint64_t *start, int64_t n_rea
     static uint8_t dummy[8];
     DISPATCH(edge_words(k), (count_edges_t<WW>(rd, (fused & 1) ? nullptr : (is_solid ? is_solid : dummy), tab, nullptr)));
     const int WE = edge_words(k);
-    DISPATCH2(key_words_s2(k), WE, (emit_edges_t<W2, WEE>(rd, tab, (fused & 1) != 0, out, (fused & 2) != 0)));
+    DISPATCH2(key_words_s2(k), WE, (emit_edges_t<W2, WEE>(rd, tab, (fused & 1) != 0, out, (fused & 2) != 0, (fused & 4) != 0)));
     *stream = (uint8_t *)malloc(out.bytes.size() + 8);
     memcpy(*stream, out.bytes.data(), out.bytes.size());
     *stream_bytes = (int64_t)out.bytes.size();

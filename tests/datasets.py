@@ -145,3 +145,24 @@ def materialise(name, directory):
         else:
             DATASETS[name](prefix)
     return prefix
+
+
+def metagenome_in_memory(n_reads, read_len, seed=20261017, **kw):
+    """The reads `synth.write_metagenome(prefix, n_reads, read_len, seed)` would write (SURVEY Appendix E.3 `gen_bin`), without
+    the file: -> (seq u32[] reversed + bit-contiguous as the reference holds them, start u64[n+1], md5 of the `.bin` bytes).
+    Chunks of 1M reads must end on a word boundary (1M * read_len % 16 == 0)."""
+    assert (1_000_000 * read_len) % 16 == 0
+    h = hashlib.md5()
+    seq = np.zeros(n_reads * read_len // 16 + 1, dtype=np.uint32)
+    at = 0
+    for c in synth.metagenome_reads(n_reads, read_len, seed, **kw):
+        h.update(synth.pack_forward(c).tobytes())
+        rev = np.ascontiguousarray(c[:, ::-1]).reshape(-1)
+        pad = (-len(rev)) % 16
+        if pad:
+            rev = np.concatenate([rev, np.zeros(pad, dtype=np.uint8)])
+        w = synth._pack_stream(rev)
+        seq[at:at + len(w)] = w
+        at += len(c) * read_len // 16
+    start = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+    return seq, start, h.hexdigest()

@@ -25,6 +25,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "sample" in line["config"]
+    assert line["reads_per_s"] > 0 and len(line["config"]["sample_hashes"]["stream_hash"]) == 16
 
 
 @pytest.mark.gpu
@@ -42,3 +43,6 @@ def test_gpu_arm_prints_the_contract_line():
         assert k in line["roofline"], k
     for k in ["value", "unit", "cores", "kind", "sample"]:
         assert k in line["cpu_baseline"], k
+    par = line["config"]["parity"]
+    assert par["sample"]["ok"] is True, par["sample"]          # GPU path == reference binary on the shared sample, in this job
+    assert len(par["stream_hash"]) == 16 and par["total_size"] == line["config"]["edges_per_step"]

@@ -178,3 +178,25 @@ def test_node_filter_drops_only_items_the_group_logic_drops(logic, read_lib, ds,
     assert n_filtered <= n_all
     if ds == "smoke" and k == 31 and m == 2 and not mercy:
         assert n_filtered < 0.5 * n_all                  # two thirds of the items are $-items, almost all of them covered
+
+
+@pytest.mark.parametrize("ds,k,m,mercy", EDGE_CASES + [("adversarial", 16, 2, False), ("adversarial", 32, 1, False), ("smoke", 30, 2, False)])
+def test_node_pass_reproduces_the_records(logic, read_lib, ds, k, m, mercy):
+    """The product's stage-2 formulation: real items from the distinct solid edges, $-items only
+    for the tip k-mers found by accumulating out / in weights per canonical k-mer (node_ops_of_edge, s2_tip_items --
+    the code k_node_part / k_node_count run).  Records, per-bucket table and totals must equal the oracle's; even k
+    exercises palindromic k-mers, k % 16 == 0 the word-boundary cases."""
+    _, rd = read_lib(ds)
+    exp_solid = None
+    if m > 1:
+        exp_solid, _, cands = O.stage1(rd, k, m, mercy)
+        if mercy:
+            O.mercy(rd, k, exp_solid, cands)
+    exp = O.stage2(rd, k, m, exp_solid)
+    logic.logic_last_items.restype = ctypes.c_int64
+    stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=4)
+    assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
+    assert logic.logic_last_items() <= 2 * int(exp[1][:, 0].sum()) + 2
+    if not mercy:
+        stream, meta, totals = run_edges(logic, rd, k, m, None, fused=5)     # multiplicities straight from the stage-1 counts
+        assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
