@@ -513,8 +513,13 @@ def main():
             kern.append(("s1.k_split", st1["ms_partition"], (4 if sharded else 2) * n1 * iw1 * 4))
             kern.append(("s1.k_count", st1["ms_sort_emit"], n1 * iw1 * 4 + rows * row_bytes))
         n2, iw2 = st2["n_items"], st2["item_words"]
+        nops, ntip = st2.get("n_node_ops", 0), st2.get("n_tip_items", 0)
+        if nops:
+            # node pass (k_node_part + k_split + k_node_count): edge rows in, ops written, split, counted; tip rows out
+            iwn = (2 * a.k + 31) // 32 + 1
+            kern.append(("s2.node_pass", st2["ms_nodes"], rows * row_bytes + 4 * nops * iwn * 4 + ntip * iw2 * 4))
         if n2:
-            kern.append(("s2.k_item_part", st2["ms_extract"], rows * row_bytes * max(1, st2["n_batches"]) + n2 * iw2 * 4))
+            kern.append(("s2.k_item_part", st2["ms_extract"], (rows * row_bytes + ntip * iw2 * 4) * max(1, st2["n_batches"]) + n2 * iw2 * 4))
             kern.append(("s2.k_split", st2["ms_partition"], 2 * n2 * iw2 * 4))
             kern.append(("s2.k_sort_emit", st2["ms_sort_emit"], n2 * iw2 * 4 + st2["out_bytes"]))
         kern.sort(key=lambda x: -x[1])

@@ -80,6 +80,10 @@ typedef struct {
     int32_t item_words;      /* u32 words per item (key + payload) */
     int32_t sort_cap;        /* items per on-chip sort tile */
     int32_t msd_levels;      /* digit partition levels that ran */
+    float ms_nodes;          /* stage 2: node pass (tip k-mers), device time */
+    int32_t reserved;
+    uint64_t n_node_ops;     /* stage 2: k-mer ops of the node pass (2 per distinct solid edge) */
+    uint64_t n_tip_items;    /* stage 2: $-items the node pass produced (2 per tip k-mer) */
 } mgta_stage_stats;
 
 int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out);

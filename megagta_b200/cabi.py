@@ -27,7 +27,8 @@ class StageStats(ctypes.Structure):
                 ("ms_total", ctypes.c_float), ("ms_hist", ctypes.c_float), ("ms_extract", ctypes.c_float),
                 ("ms_partition", ctypes.c_float), ("ms_sort_emit", ctypes.c_float),
                 ("key_words", ctypes.c_int32), ("item_words", ctypes.c_int32), ("sort_cap", ctypes.c_int32),
-                ("msd_levels", ctypes.c_int32)]
+                ("msd_levels", ctypes.c_int32), ("ms_nodes", ctypes.c_float), ("reserved", ctypes.c_int32),
+                ("n_node_ops", ctypes.c_uint64), ("n_tip_items", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -20,6 +20,7 @@
 #include "v2_kernels.cuh"
 #include "emit_kernels.cuh"
 #include "mercy_kernels.cuh"
+#include "node_kernels.cuh"
 
 using namespace mgta;
 
@@ -29,7 +30,7 @@ std::string g_create_error;
 
 enum { CTR_TICKET = 0, CTR_NLIST0 = 1, CTR_NLIST1 = 2, CTR_NGIANTS = 3, CTR_ERR = 4, CTR_TICKET2 = 5, CTR_TICKET3 = 6, CTR_NOVF = 7,
        CTR_NOVF2 = 8, CTR_COUNT = 12 };
-enum { PH_HIST = 0, PH_EXTRACT = 1, PH_PARTITION = 2, PH_SORT = 3, PH_COUNT = 4 };
+enum { PH_HIST = 0, PH_EXTRACT = 1, PH_PARTITION = 2, PH_SORT = 3, PH_NODES = 4, PH_COUNT = 5 };
 
 struct Timed {
     int phase;
@@ -78,6 +79,7 @@ struct mgta_ctx {
     // arena
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0;
+    size_t budget_cached = 0;              // see hbm_budget()
     // results
     std::vector<int64_t> hist;             // last histogram (whole bucket space)
     int shard_lo = 0, shard_hi = NUM_BUCKETS;
@@ -114,6 +116,12 @@ struct mgta_ctx {
     unsigned long long *d_cand = nullptr;
     uint64_t cand_cap = 0, n_cand = 0, num_mercy = 0;
     bool mercy_valid = false;
+    // node pass (stage 2): the $-items of the tip k-mers, rows of key_words_s2 + 1 words; see node_kernels.cuh
+    bool node_pass = false;
+    uint32_t *d_tips = nullptr;
+    uint64_t n_tips = 0, tips_cap = 0;
+    bool tips_valid = false;
+    uint32_t *d_hist_bak = nullptr;        // d_hist_s2 before the node pass added the tip items (restored when the pass restarts)
 };
 
 // Host waits on the context's stream.  A blocking cudaStreamSynchronize puts the thread to sleep; on a loaded host the
@@ -250,7 +258,7 @@ size_t carve(Plan &pl, uint64_t cap, uint64_t n_dollar) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int mgta_abi_version(void) { return 2; }
+extern "C" int mgta_abi_version(void) { return 3; }
 
 extern "C" int mgta_words_per_key(int stage, int kmer_k) { return stage == 1 ? key_words_s1(kmer_k) : key_words_s2(kmer_k); }
 
@@ -305,6 +313,11 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
         if (const char *e2 = getenv("MGTA_S2_PB")) ctx->PB = std::max(16, std::min(std::min(atoi(e2), 24), 2 * (opts->kmer_k - 1)));   // test hook
     }
     if ((e = cudaMalloc(&ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_hist_bak, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    // one shard: stage 2 takes its $-items from the node pass (a third of the items to partition and sort); several
+    // shards still exchange whole edge lists and generate every item (MGTA_NODE_PASS=0/1 overrides, A/B switch)
+    ctx->node_pass = opts->world == 1;
+    if (const char *e3 = getenv("MGTA_NODE_PASS")) ctx->node_pass = atoi(e3) != 0 && opts->world == 1;
     if ((e = cudaHostAlloc(&ctx->h_hist2, ((size_t)1 << ctx->PB) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaMalloc(&ctx->d_xs, (size_t)(MAX_OWNERS + 1) * 24)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
@@ -319,7 +332,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
-    cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs); cudaFree(ctx->d_cand);
+    cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs); cudaFree(ctx->d_cand); cudaFree(ctx->d_tips); cudaFree(ctx->d_hist_bak);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_hist2);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -356,6 +369,7 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
         CK(cudaMalloc(&ctx->d_seq, padded * 4));
         CK(cudaMalloc(&ctx->d_start, (n_reads + 1) * 8));
         CK(cudaMalloc(&ctx->d_solid, solid_words * 4));
+        ctx->budget_cached = 0;
     }
     ctx->solid_words = solid_words;
     CK(cudaMemsetAsync(ctx->d_seq + n_words, 0, (padded - n_words) * 4, ctx->stream));
@@ -520,6 +534,7 @@ int finish_timing(mgta_ctx *ctx, mgta_stage_stats *st) {
             case PH_EXTRACT: st->ms_extract += ms; break;
             case PH_PARTITION: st->ms_partition += ms; break;
             case PH_SORT: st->ms_sort_emit += ms; break;
+            case PH_NODES: st->ms_nodes += ms; break;
             default: break;
         }
         cudaEventDestroy(t.a);
@@ -535,22 +550,34 @@ struct Carver {
     size_t take(size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; }
 };
 
+// HBM budget of the context: --gpu_mem, or 90 % of what is free plus what the arena already holds.  cudaMemGetInfo goes
+// through the kernel driver and was measured to stall for tens of milliseconds on a busy host -- with the GPU idle, at the
+// start of every stage -- so the value is cached and refreshed only when the arena has to grow (the stream is drained
+// there anyway).
+size_t hbm_budget(mgta_ctx *ctx, bool refresh = false) {
+    if (ctx->opt.hbm_budget_bytes > 0) return (size_t)ctx->opt.hbm_budget_bytes;
+    if (!ctx->budget_cached || refresh) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        ctx->budget_cached = (size_t)(0.9 * (double)(free_b + ctx->arena_bytes));
+    }
+    return ctx->budget_cached;
+}
+
 int ensure_arena(mgta_ctx *ctx, size_t bytes) {
     if (bytes > ctx->arena_bytes) {
         CK(mgta_stream_wait(ctx->stream));
         cudaFree(ctx->arena);
         ctx->arena = nullptr; ctx->arena_bytes = 0;
-        CK(cudaMalloc(&ctx->arena, bytes));
+        if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            const size_t now = hbm_budget(ctx, true);      // the cached budget was stale (other buffers grew since)
+            FAIL(MGTA_ERR_MEM, "cannot allocate a %zu B arena (budget now %zu B): call again, the plan will use the smaller budget", bytes, now);
+        }
         ctx->arena_bytes = bytes;
+        hbm_budget(ctx, true);
     }
     return MGTA_OK;
-}
-
-size_t hbm_budget(mgta_ctx *ctx) {
-    if (ctx->opt.hbm_budget_bytes > 0) return (size_t)ctx->opt.hbm_budget_bytes;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    return (size_t)(0.9 * (double)(free_b + ctx->arena_bytes));
 }
 
 int count_positions(mgta_ctx *ctx) {
@@ -627,16 +654,67 @@ int launch_count(int WE, bool plus, const CountParams &P, unsigned grid, size_t 
     return e == cudaSuccess ? 0 : -1;
 }
 
-int launch_item_part(int WE, bool plus, const ItemPartParams &P, unsigned grid, cudaStream_t st) {
+template <int PER>
+int launch_item_part_t(int WE, bool plus, const ItemPartParams &P, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
+    const unsigned per_cta = ITEM_SLOTS / PER;
+    const unsigned grid = (unsigned)((P.n_edges + per_cta - 1) / per_cta);
     WE_SWITCH(WE, {
-        const size_t smem = bin_smem_bytes(EE + (plus ? 1 : 0) + 1, ITEM_EDGES * 6);
+        const size_t smem = bin_smem_bytes(EE + (plus ? 1 : 0) + 1, ITEM_SLOTS);
         if (plus) {
-            e = cudaFuncSetAttribute(k_item_part<EE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k_item_part<EE, true><<<grid, PART_THREADS, smem, st>>>(P);
+            e = cudaFuncSetAttribute(k_item_part<EE, true, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_item_part<EE, true, PER><<<grid, PART_THREADS, smem, st>>>(P);
         } else {
-            e = cudaFuncSetAttribute(k_item_part<EE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k_item_part<EE, false><<<grid, PART_THREADS, smem, st>>>(P);
+            e = cudaFuncSetAttribute(k_item_part<EE, false, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_item_part<EE, false, PER><<<grid, PART_THREADS, smem, st>>>(P);
+        }
+    });
+    return e == cudaSuccess ? 0 : -1;
+}
+
+// real_only: the two real items per edge (the node pass supplies the $-items); else all six
+int launch_item_part(int WE, bool plus, bool real_only, const ItemPartParams &P, cudaStream_t st) {
+    return real_only ? launch_item_part_t<2>(WE, plus, P, st) : launch_item_part_t<6>(WE, plus, P, st);
+}
+
+#define KW_SWITCH(KW, ...)                                         \
+    switch (KW) {                                                  \
+        case 1: { constexpr int KK = 1; __VA_ARGS__; } break;      \
+        case 2: { constexpr int KK = 2; __VA_ARGS__; } break;      \
+        case 3: { constexpr int KK = 3; __VA_ARGS__; } break;      \
+        case 4: { constexpr int KK = 4; __VA_ARGS__; } break;      \
+        case 5: { constexpr int KK = 5; __VA_ARGS__; } break;      \
+        case 6: { constexpr int KK = 6; __VA_ARGS__; } break;      \
+        case 7: { constexpr int KK = 7; __VA_ARGS__; } break;      \
+        case 8: { constexpr int KK = 8; __VA_ARGS__; } break;      \
+        default: break;                                            \
+    }
+
+int launch_node_part(int KW, bool eplus, const NodePartParams &P, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    const unsigned grid = (unsigned)((P.n_edges + NODE_EDGES - 1) / NODE_EDGES);
+    KW_SWITCH(KW, {
+        const size_t smem = bin_smem_bytes(KK + 1, NODE_EDGES * 2);
+        if (eplus) {
+            e = cudaFuncSetAttribute(k_node_part<KK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_node_part<KK, true><<<grid, PART_THREADS, smem, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(k_node_part<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_node_part<KK, false><<<grid, PART_THREADS, smem, st>>>(P);
+        }
+    });
+    return e == cudaSuccess ? 0 : -1;
+}
+
+int launch_node_count(int KW, bool plus, const NodeCountParams &P, unsigned grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    KW_SWITCH(KW, {
+        if (plus) {
+            e = cudaFuncSetAttribute(k_node_count<KK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_node_count<KK, true><<<grid, COUNT_THREADS, smem, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(k_node_count<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_node_count<KK, false><<<grid, COUNT_THREADS, smem, st>>>(P);
         }
     });
     return e == cudaSuccess ? 0 : -1;
@@ -803,7 +881,7 @@ int count_batch_tail(mgta_ctx *ctx, const CountPlan &cp, const CountLay &L, unsi
     CP.emit = cp.mark_mode ? 0 : 1;
     CP.solid = ctx->d_solid; CP.edge_counting = (cp.stage1_mode && !cp.mark_mode) ? ctx->d_ec : nullptr;
     CP.edges_out = bufA; CP.n_edges = ctx->d_totals + 14; CP.edges_cap = (uint64_t)IW * L.capA / (WE + 1);
-    CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
+    CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB; CP.real_only = ctx->node_pass ? 1 : 0;
     CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = L.NT;
     CP.err = ctx->d_ctr + CTR_ERR;
     if ((rc = begin_timed(ctx, PH_SORT))) return rc;
@@ -876,6 +954,8 @@ int count_reset_outputs(mgta_ctx *ctx, const CountPlan &cp) {
     } else {
         ctx->n_edges = 0;
         ctx->edges_all_valid = false;
+        ctx->tips_valid = false;
+        ctx->n_tips = 0;
         CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
         if (cp.stage1_mode) CK(cudaMemsetAsync(ctx->d_ec, 0, NUM_BUCKETS * 8, ctx->stream));
     }
@@ -1335,6 +1415,141 @@ int ensure_solid(mgta_ctx *ctx) {
     return finish_timing(ctx, &dummy);
 }
 
+// ---- the node pass of stage 2 (node_kernels.cuh) ----------------------------------------------------------
+// {(canonical edge, multiplicity)} -> 2 ops per edge keyed by canonical k-mer -> two hash partition levels -> per-tile
+// tables of (out, in) weights -> the $-items of the tip k-mers (ctx->d_tips) + their share of the stage-2 histogram.
+int run_nodes(mgta_ctx *ctx, mgta_stage_stats *st) {
+    const int k = ctx->opt.kmer_k, KW = kmer_words(k), WE = edge_words(k), W2 = key_words_s2(k), IW = KW + 1;
+    const bool eplus = WE > KW, plus2 = W2 > KW;
+    int rc;
+    ctx->tips_valid = false;
+    ctx->n_tips = 0;
+    const uint64_t n_edges = ctx->n_edges, n_ops = 2 * n_edges;
+    st->n_node_ops = n_ops;
+    st->n_tip_items = 0;
+    if (n_edges == 0) { ctx->tips_valid = true; return MGTA_OK; }
+    CountPlan cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.k = k; cp.WE = KW; cp.PW = 1; cp.IW = IW; cp.has_assist = true; cp.stage1_mode = true; cp.n_pos = n_ops;
+    const size_t slot_bytes = 4 * (size_t)(3 + KW) + 2;
+    cp.tab_cap = 4096; cp.big_cap = 16384;
+    while (cp.tab_cap > 1024 && cp.tab_cap * slot_bytes > 106 * 1024) cp.tab_cap >>= 1;
+    while (cp.big_cap > cp.tab_cap && cp.big_cap * slot_bytes > 200 * 1024) cp.big_cap >>= 1;
+    cp.tab_limit = cp.tab_cap - 640;
+    if (ctx->opt.sort_items_cap > 0) cp.tab_limit = std::min<unsigned>(cp.tab_limit, std::max(8, ctx->opt.sort_items_cap));   // test hook
+    int bits = 2;
+    while (bits < 28 && (n_ops >> bits) > (uint64_t)cp.tab_cap * 3 / 4) ++bits;
+    cp.bits = bits;
+    cp.lb2 = (unsigned)std::min(10, bits / 2);
+    cp.lb1 = (unsigned)bits - cp.lb2;
+    cp.B1 = 1u << cp.lb1;
+    cp.T = split_chunk_items(IW);
+    cp.r_lo = 0; cp.r_hi = cp.B1;
+    const size_t smem_count = count_smem_bytes(KW, cp.tab_cap, 1), smem_big = count_smem_bytes(KW, cp.big_cap, 1);
+    const size_t budget = hbm_budget(ctx);
+    const size_t row = (size_t)(W2 + 1) * 4;
+    CK(cudaMemcpyAsync(ctx->d_hist_bak, ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    uint64_t tips_cap = std::max<uint64_t>(ctx->tips_cap, std::max<uint64_t>(1u << 20, n_edges / 4));
+    double slack = 1.15;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt >= 10) FAIL(MGTA_ERR_MEM, "node pass: the partition does not settle");
+        if (attempt) CK(cudaMemcpyAsync(ctx->d_hist_s2, ctx->d_hist_bak, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (tips_cap > ctx->tips_cap || !ctx->d_tips) {
+            CK(mgta_stream_wait(ctx->stream));
+            cudaFree(ctx->d_tips);
+            ctx->d_tips = nullptr; ctx->tips_cap = 0;
+            CK(cudaMalloc(&ctx->d_tips, tips_cap * row));
+            ctx->tips_cap = tips_cap;
+        }
+        CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));                  // tip rows (free after the mercy pass of stage 1)
+        bool retry = false;
+        CountLay L;
+        unsigned n_batches = (cp.B1 + MAX_BINS - 1) / MAX_BINS;
+        count_layout(cp, L, n_batches, slack, 0, 0, 0);
+        while (L.total > budget && L.bins > 1) { n_batches *= 2; count_layout(cp, L, n_batches, slack, 0, 0, 0); }
+        if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 bin of the node pass (%zu B)", budget, L.total);
+        if ((rc = ensure_arena(ctx, L.total))) return rc;
+        uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
+        uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+        unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+        unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
+        for (unsigned batch = 0; batch < n_batches && !retry; ++batch) {
+            const unsigned b_lo = batch * L.bins, b_hi = std::min(cp.B1, b_lo + L.bins);
+            if (b_lo >= b_hi) break;
+            if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) return rc;
+            if ((rc = begin_timed(ctx, PH_NODES))) return rc;
+            NodePartParams NP;
+            memset(&NP, 0, sizeof(NP));
+            NP.edges = ctx->d_edges; NP.n_edges = n_edges; NP.k = k; NP.sh1 = 32 - (int)cp.lb1; NP.sh2 = 32 - cp.bits; NP.lb2 = cp.lb2;
+            NP.b_lo = b_lo; NP.b_hi = b_hi; NP.cursor1 = cur1; NP.slab_cap = L.slab_cap; NP.hist2 = hist2; NP.dst = bufA; NP.cap = L.capA;
+            NP.err = ctx->d_ctr + CTR_ERR;
+            if (launch_node_part(KW, eplus, NP, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_node_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            ScanParams SP;
+            memset(&SP, 0, sizeof(SP));
+            const unsigned NTb = (b_hi - b_lo) << cp.lb2;
+            SP.hist = hist2; SP.NT = NTb; SP.lb2 = cp.lb2; SP.t_lo = 0; SP.t_hi = NTb;
+            SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
+            SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
+            SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
+            SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
+            SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
+            SP.T = cp.T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
+            SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
+            if ((rc = launch_scans(ctx, SP))) return rc;
+            SplitParams XP;
+            memset(&XP, 0, sizeof(XP));
+            XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = IW; XP.WE = KW; XP.mode = 0;
+            XP.sh2 = 32 - cp.bits; XP.lb2 = cp.lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
+            XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
+            if ((rc = launch_split(ctx, XP))) return rc;
+            NodeCountParams CP;
+            memset(&CP, 0, sizeof(CP));
+            CP.src = bufB; CP.cap = L.capB; CP.k = k; CP.off2 = off2; CP.t_lo = 0; CP.t_hi = NTb; CP.ticket = ctx->d_ctr + CTR_TICKET2;
+            CP.tab_cap = cp.tab_cap; CP.tab_limit = cp.tab_limit; CP.tips_out = ctx->d_tips; CP.n_tips = ctx->d_totals + 11;
+            CP.tips_cap = ctx->tips_cap; CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
+            CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = L.NT;
+            CP.err = ctx->d_ctr + CTR_ERR;
+            if (launch_node_count(KW, plus2, CP, (unsigned)(ctx->sm_count * 2), smem_count, ctx->stream))
+                FAIL(MGTA_ERR_CUDA, "k_node_count launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            NodeCountParams CB = CP;                                                     // overflow tiles: one CTA per SM, large table
+            CB.tile_list = CP.ovf_list; CB.n_tile_list = CP.n_ovf; CB.ticket = ctx->d_ctr + CTR_TICKET3;
+            CB.tab_cap = cp.big_cap; CB.tab_limit = cp.big_cap - 1024; CB.ovf_cap = 0; CB.n_ovf = ctx->d_ctr + CTR_NOVF2;
+            if (launch_node_count(KW, plus2, CB, (unsigned)ctx->sm_count, smem_big, ctx->stream))
+                FAIL(MGTA_ERR_CUDA, "k_node_count (overflow pass) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            if ((rc = end_timed(ctx))) return rc;
+            st->n_launches += 7;
+            unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+            unsigned long long *h_nt = ctx->h_pin + 2 * NUM_BUCKETS + 8;
+            CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_nt, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(mgta_stream_wait(ctx->stream));
+            const unsigned dev_err = h_ctr[CTR_ERR];
+            if (dev_err & ERR_SLAB_OVERFLOW) {
+                std::vector<unsigned long long> hc(b_hi - b_lo);
+                CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long mx = 0;
+                for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
+                slack = std::max(slack * 1.5, (double)mx / ((double)n_ops / cp.B1) * 1.05);
+                retry = true;
+                break;
+            }
+            if (dev_err & ERR_EDGE_LIST_FULL) {                     // the tip list was too small: the counter kept counting
+                tips_cap = std::max<uint64_t>(2 * ctx->tips_cap, (uint64_t)((double)h_nt[0] * n_batches / (batch + 1) * 1.1) + 1024);
+                retry = true;
+                break;
+            }
+            if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (node pass, bins [%u,%u))", dev_err, b_lo, b_hi);
+            ctx->n_tips = h_nt[0];
+        }
+        if (!retry) break;
+    }
+    st->n_tip_items = ctx->n_tips;
+    ctx->tips_valid = true;
+    return MGTA_OK;
+}
+
 // ---- the emission pipeline -------------------------------------------------------------------------
 // {(canonical edge, multiplicity)} -> stage-2 items (S a | flags, multiplicity) -> two key-prefix partition levels
 // (exact offsets) -> per-window on-chip sort + W/last/tip/multiplicity records (k_sort_emit) -> sink.
@@ -1377,8 +1592,9 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
 
     const size_t budget = hbm_budget(ctx);
     struct Lay { size_t A, B, flags, win, state, list0, list1, giants, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, out, tmp, total; } L;
+    const bool tips_in = ctx->node_pass && ctx->tips_valid && !ctx->edges_all_valid;   // $-items come from the node pass
     auto layout = [&](uint64_t cap) {
-        carve(pl, cap, cap / 3 + 1);
+        carve(pl, cap, tips_in ? ctx->n_tips : cap / 3 + 1);
         Carver c;
         L.A = c.take((size_t)IW * pl.cap * 4); L.B = c.take((size_t)IW * pl.cap * 4);
         L.flags = c.take((pl.cap / 32 + 64) * 4);
@@ -1472,9 +1688,20 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = nb1; IP.b1_lo = g1_lo; IP.dst = bufA; IP.cap = pl.cap;
         IP.err = ctx->d_ctr + CTR_ERR;
         if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
-        if (launch_item_part(WE, plus, IP, (unsigned)((IP.n_edges + ITEM_EDGES - 1) / ITEM_EDGES), ctx->stream))
+        if (launch_item_part(WE, plus, tips_in, IP, ctx->stream))
             FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         CK(cudaGetLastError());
+        if (tips_in && ctx->n_tips) {
+            RowPartParams RP;
+            memset(&RP, 0, sizeof(RP));
+            RP.rows = ctx->d_tips; RP.n_rows = ctx->n_tips; RP.IW = IW; RP.sh1 = IP.sh1; RP.bkt_lo = IP.bkt_lo; RP.bkt_hi = IP.bkt_hi;
+            RP.cursor1 = IP.cursor1; RP.NB = IP.NB; RP.b1_lo = IP.b1_lo; RP.dst = IP.dst; RP.cap = IP.cap; RP.err = IP.err;
+            const size_t smem = bin_smem_bytes(IW, ROW_SLOTS);
+            CK(cudaFuncSetAttribute(k_row_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_row_part<<<(unsigned)((ctx->n_tips + ROW_SLOTS - 1) / ROW_SLOTS), PART_THREADS, smem, ctx->stream>>>(RP);
+            CK(cudaGetLastError());
+            st->n_launches++;
+        }
         if ((rc = end_timed(ctx))) return rc;
         // ---- K3a: level-2 prefix split, leaf flags, MSD levels for oversize tiles
         SplitParams XP;
@@ -1759,6 +1986,9 @@ extern "C" int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts, int
 extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals) {
     if (!ctx) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
+    // several shards: this shard's edge list alone would give a self-consistent but partial graph
+    if (ctx->opt.world > 1 && ctx->edges_valid && !ctx->edges_all_valid)
+        FAIL(MGTA_ERR_STATE, "stage 2 on %d shards needs the solid edges of all shards: exchange them (mgta_edges_reserve) first", ctx->opt.world);
     mgta_stage_stats *st = &ctx->stats[1];
     StageTimer tm;
     int rc = stage_begin(ctx, st, tm);
@@ -1771,7 +2001,9 @@ extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int
         if ((rc = run_count(ctx, CM_GENERAL, &tmp))) return rc;
         st->n_launches += tmp.n_launches;
     }
+    if (ctx->node_pass && !ctx->edges_all_valid && !ctx->tips_valid && (rc = run_nodes(ctx, st))) return rc;
     if ((rc = run_emit(ctx, sink, user, totals, st))) return rc;
+    if (ctx->node_pass && ctx->tips_valid) { st->n_node_ops = 2 * ctx->n_edges; st->n_tip_items = ctx->n_tips; }
     return stage_end(ctx, st, tm);
 }
 

@@ -74,9 +74,10 @@ def test_gpu_small_tables_force_the_overflow_pass(read_lib, ds, k, m, cap):
         assert got["stats1"]["msd_levels"] >= 1          # overflow tiles of the counting pass
 
 
-def test_gpu_small_sort_tiles_force_msd_levels(golden, read_lib):
+def test_gpu_small_sort_tiles_force_msd_levels(golden, read_lib, monkeypatch):
     g = golden["cases"]["meta200k_k31_m2"]
     _, rd = read_lib(g["dataset"])
+    monkeypatch.setenv("MGTA_S2_PB", "16")               # one prefix tile per lv1 bucket: ~38 items against leaves of 32
     got = run_gpu(rd, g["k"], g["m"], sort_items_cap=64)
     check_vs_golden(got, g)
     assert got["stats2"]["msd_levels"] >= 1
