@@ -53,8 +53,6 @@ def parse():
     ap.add_argument("--phases", action="store_true", help="diagnostic: per-phase host wall times of every rank on stderr (adds syncs)")
     ap.add_argument("--root-upload", action="store_true",
                     help="N>1: rank 0 uploads all reads and broadcasts them (default: every rank uploads its slice, NCCL all-gather)")
-    ap.add_argument("--replicated-scan", action="store_true",
-                    help="N>1: every shard scans ALL reads for its hash range (no item all-to-all); default is the scan-sharded stage 1")
     a = ap.parse_args()
     if a.total_reads:
         assert a.total_reads % (a.gpus * 1_000_000) == 0, "--total-reads must be a multiple of 1M x GPUs"
@@ -380,11 +378,6 @@ def main():
             dist.broadcast(torch.as_tensor(DevBuf(tp, tb), device=dev), 0)
         return h2d
 
-    def exchange_edges():
-        """world > 1: all-gather of the solid-edge rows + all-reduce of the stage-2 prefix histogram."""
-        if world > 1:
-            shards.exchange_ctx(ctx, rank, world, dist, dev)
-
     phases = {}
 
     def mark(name, t0):
@@ -394,25 +387,25 @@ def main():
         phases.setdefault(name, []).append(round((time.time() - t0) * 1000, 1))
         return time.time()
 
+    comm = shards.TorchComm(ctx, rank, world, dist, dev) if world > 1 else None
+
     def step(e2e):
-        """-> (edges of this shard, h2d bytes, d2h bytes)"""
+        """-> (edges of this shard, h2d bytes, d2h bytes).  N > 1: the library walks the sharded protocol
+        (mgta_sharded_begin / _step), TorchComm runs the collectives it asks for over NCCL."""
         t = time.time()
         h2d = load_reads() if e2e else 0
         t = mark("load", t)
         d2h = 0
         if a.m > 1:
-            if world > 1 and not a.replicated_scan:
-                shards.stage1_scan_sharded(ctx, n_reads, rank, world, dist, dev)
+            if world > 1:
+                ctx.sharded(1, comm)
             else:
                 ctx.stage1()
             t = mark("stage1", t)
-            exchange_edges()
-            t = mark("edge_exchange", t)
+        collect = "count" if e2e else False
+        nbytes, meta, totals = ctx.sharded(2, comm, collect=collect) if world > 1 else ctx.stage2(collect=collect)
         if e2e:
-            nbytes, meta, totals = ctx.stage2(collect="count")
             d2h = nbytes + meta[slice(*ctx.shard_range())].nbytes
-        else:
-            ctx.stage2(collect=False)
         mark("stage2", t)
         return ctx.stats(2)["n_edges"], h2d, d2h
 
@@ -458,7 +451,7 @@ def main():
     wpt = (2 * a.k + 31) // 32
     if not a.no_hash:
         with torch.cuda.stream(stream):
-            h_stream, h_meta, h_totals = ctx.stage2(collect=True)
+            h_stream, h_meta, h_totals = ctx.sharded(2, comm, collect=True) if world > 1 else ctx.stage2(collect=True)
         xs = bucket_xsum(h_stream, h_meta, wpt)
         part = torch.tensor([xs & 0xFFFFFFFF, xs >> 32, len(h_stream), int(h_meta[:, 0].sum()), int(h_meta[:, 1].sum())], dtype=torch.int64, device=dev)
         if world > 1:
@@ -508,7 +501,7 @@ def main():
         n1, iw1, rows = st1["n_items"], st1["item_words"], st1["n_edges"]
         row_bytes = (st1["key_words"] + 1) * 4
         if n1:
-            sharded = world > 1 and not a.replicated_scan
+            sharded = world > 1
             kern.append(("s1.k_edge_part", st1["ms_extract"], (seq_bytes // world if sharded else seq_bytes * max(1, st1["n_batches"])) + n1 * iw1 * 4))
             kern.append(("s1.k_split", st1["ms_partition"], (4 if sharded else 2) * n1 * iw1 * 4))
             kern.append(("s1.k_count", st1["ms_sort_emit"], n1 * iw1 * 4 + rows * row_bytes))
@@ -601,7 +594,7 @@ def main():
                            "s2_items": total_items(st2, world, dist, dev, torch),
                            "l2": "inputs larger than L2 (item arrays are GBs per step); no explicit flush",
                            "sharding": "contiguous lv1-bucket ranges, %d shard(s)" % world,
-                           "stage1": ("one shard" if world == 1 else "replicated scan, hash-range shards" if a.replicated_scan
+                           "stage1": ("one shard" if world == 1
                                       else "scan-sharded: each shard scans 1/N of the reads, NCCL all-to-all of the items by hash owner"),
                            "upload": ("rank 0 H2D" + (" + NCCL broadcast" if world > 1 else "") if not sharded_upload
                                       else "every rank H2D of its slice + NCCL all-gather"),

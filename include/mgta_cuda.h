@@ -180,6 +180,52 @@ int mgta_get_mercy_candidates(mgta_ctx *ctx, uint64_t *host, uint64_t cap, uint6
 /* Number of is_solid bits the per-read mercy scan added (the reference logs it as "Number mercy", s2.cpp:241). */
 int mgta_get_num_mercy(mgta_ctx *ctx, uint64_t *num_mercy);
 
+/* ---- Sharded build, world > 1: the protocol lives in the library, the caller only runs collectives ----------------------
+ * One context per GPU (rank r of world), one caller thread or process per context.  Every context holds ALL reads
+ * (upload 1/world each + all-gather, or broadcast: mgta_alloc_reads / mgta_reads_device_buffers).  Then, per stage:
+ *
+ *     mgta_sharded_begin(ctx, stage, sink, user);
+ *     for (;;) {
+ *         mgta_collective c;
+ *         mgta_sharded_step(ctx, &c);            // runs this shard's kernels up to the next exchange
+ *         if (c.op == MGTA_COLL_NONE) break;     // stage finished
+ *         <run collective c among the `world` contexts, ordered on the context's stream>
+ *     }
+ *     mgta_sharded_result(ctx, edge_counting, totals);
+ *
+ * All ranks see the same sequence of collectives.  Buffers are device memory owned by the library.  The collective must
+ * be enqueued on (or otherwise ordered with) the stream of the context (mgta_opts.stream): the library launches the
+ * kernels that produce `send` and consume `recv` on that stream and does not synchronise with any other.
+ *   ALL_TO_ALL     send / recv hold `world` slabs of `bytes` bytes: slab d of send goes to rank d, slab s of recv comes
+ *                  from rank s (ncclSend / ncclRecv in one group; torch.distributed.all_to_all_single)
+ *   ALL_GATHER     every rank contributes `bytes` bytes at send == recv + rank * bytes (in place); recv holds world * bytes
+ *   ALL_REDUCE_*   in place (send == recv), `bytes` / 4 resp. / 8 elements, operator SUM
+ * Stage 1 replaces cx1.run() with the s1 callbacks (build_graph.cpp:100-113): scan-sharded extraction, all-to-all of the
+ * (k+1)-mer items by hash owner, counting; edge_counting is all-reduced, every rank gets the whole array.  Stage 2
+ * replaces the s2 run (build_graph.cpp:120-132): exchange of the solid edges, then every rank emits its lv1-bucket
+ * range to its sink (ascending buckets; ranks in order give the whole graph). */
+typedef enum {
+    MGTA_COLL_NONE = 0,
+    MGTA_COLL_ALL_TO_ALL = 1,
+    MGTA_COLL_ALL_GATHER = 2,
+    MGTA_COLL_ALL_REDUCE_SUM_U32 = 3,
+    MGTA_COLL_ALL_REDUCE_SUM_U64 = 4
+} mgta_coll_op;
+
+typedef struct {
+    int32_t op;       /* mgta_coll_op */
+    int32_t reserved;
+    void *send;       /* device */
+    void *recv;       /* device */
+    uint64_t bytes;   /* see above */
+} mgta_collective;
+
+int mgta_sharded_begin(mgta_ctx *ctx, int stage /*1|2*/, mgta_bucket_sink sink, void *user);
+int mgta_sharded_step(mgta_ctx *ctx, mgta_collective *next);
+/* after the stage finished: stage 1 -> edge_counting int64[65536] (whole graph, may be NULL);
+ * stage 2 -> totals int64[10] of THIS shard (may be NULL; sum over the shards) */
+int mgta_sharded_result(mgta_ctx *ctx, int64_t *edge_counting, int64_t *totals);
+
 /* Stage 2 (cx1.run() with the s2 callbacks + SdbgWriter): emits this shard's buckets in ascending
  * order.  sink may be NULL (device-resident run: records are produced and counted, not copied).
  * totals: int64[10] = num_w[0..8], num_last1 (sdbg_multi_io.h:114-143); may be NULL. */

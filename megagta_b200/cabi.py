@@ -34,6 +34,14 @@ class StageStats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Collective(ctypes.Structure):
+    """mgta_collective: the exchange the library asks the caller to run among the shards (include/mgta_cuda.h)"""
+    _fields_ = [("op", ctypes.c_int32), ("reserved", ctypes.c_int32), ("send", ctypes.c_void_p), ("recv", ctypes.c_void_p),
+                ("bytes", ctypes.c_uint64)]
+
+
+COLL_NONE, COLL_ALL_TO_ALL, COLL_ALL_GATHER, COLL_ALL_REDUCE_SUM_U32, COLL_ALL_REDUCE_SUM_U64 = 0, 1, 2, 3, 4
+
 SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                         ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64))
 
@@ -43,7 +51,7 @@ EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_r
            "mgta_stage1_slab_items", "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
            "mgta_get_mercy_candidates", "mgta_get_num_mercy", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
            "mgta_edge_hist_device_buffer", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
-           "mgta_abi_version"]
+           "mgta_abi_version", "mgta_sharded_begin", "mgta_sharded_step", "mgta_sharded_result"]
 
 _lib = None
 
@@ -92,6 +100,9 @@ def load():
                                                      ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_shard_range.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
         lib.mgta_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(StageStats)]
+        lib.mgta_sharded_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, SINK, ctypes.c_void_p]
+        lib.mgta_sharded_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(Collective)]
+        lib.mgta_sharded_result.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -248,6 +259,48 @@ class Context:
         totals = np.zeros(10, dtype=np.int64)
         self._check(self.lib.mgta_stage2(self.h, cb, None, _p(totals)), "mgta_stage2")
         return (b"".join(parts) if collect is True else nbytes_total[0]), meta, totals
+
+    # ---- sharded build (world > 1): the library walks the protocol, the caller runs the collectives it asks for
+    def sharded_begin(self, stage, collect=True):
+        """collect: as in stage2() (stage 2 only)"""
+        self._sh = {"stage": stage, "collect": collect, "parts": [], "nbytes": 0, "meta": np.zeros((NUM_BUCKETS, 3), dtype=np.int64)}
+        sh = self._sh
+
+        def sink(user, b0, b1, ptr, nbytes, mptr):
+            if nbytes and collect is True:
+                sh["parts"].append(ctypes.string_at(ptr, nbytes))
+            sh["nbytes"] += nbytes
+            sh["meta"][b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
+            return 0
+
+        sh["cb"] = SINK(sink) if (collect and stage == 2) else ctypes.cast(None, SINK)      # kept alive until the result is read
+        self._check(self.lib.mgta_sharded_begin(self.h, stage, sh["cb"], None), "mgta_sharded_begin")
+
+    def sharded_step(self):
+        """-> Collective to run among the shards on this context's stream, or None when the stage has finished"""
+        c = Collective()
+        self._check(self.lib.mgta_sharded_step(self.h, ctypes.byref(c)), "mgta_sharded_step")
+        return None if c.op == COLL_NONE else c
+
+    def sharded_result(self):
+        """stage 1 -> edge_counting int64[65536] of the whole graph; stage 2 -> (stream | byte count, meta, totals) of this shard"""
+        sh = self._sh
+        if sh["stage"] == 1:
+            ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
+            self._check(self.lib.mgta_sharded_result(self.h, _p(ec), None), "mgta_sharded_result")
+            return ec
+        totals = np.zeros(10, dtype=np.int64)
+        self._check(self.lib.mgta_sharded_result(self.h, None, _p(totals)), "mgta_sharded_result")
+        return (b"".join(sh["parts"]) if sh["collect"] is True else sh["nbytes"]), sh["meta"], totals
+
+    def sharded(self, stage, run_collective, collect=True):
+        """One whole stage: run_collective(Collective) executes an exchange among the shards (see shards.TorchComm)."""
+        self.sharded_begin(stage, collect)
+        while True:
+            c = self.sharded_step()
+            if c is None:
+                return self.sharded_result()
+            run_collective(c)
 
     def edges_local(self):
         """-> (device pointer, rows, u32 words per row) of this shard's solid-edge list"""

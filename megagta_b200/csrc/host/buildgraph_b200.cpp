@@ -17,10 +17,15 @@
 #include <string.h>
 #include <zlib.h>
 #include <omp.h>
+#include <unistd.h>
 #include <chrono>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <cuda_runtime_api.h>      // device count, streams, pinned host memory: plumbing only, every kernel sits behind the C ABI
+#include <nccl.h>
 
 #include "../../../include/mgta_cuda.h"
 
@@ -102,14 +107,29 @@ Options parse(int argc, char **argv) {
 // ---- read library -> reversed, bit-contiguous packed reads (what ReadBinaryLibs(..., is_reverse = true) builds:
 // read_lib_functions-inl.h:233-261, SequencePackage::AppendRevSeq sequence_package.h:247-252,341-367)
 struct Reads {
-    uint32_t *seq = nullptr;           // malloc'ed, n_words
+    uint32_t *seq = nullptr;           // n_words (+ slack), zero initialised; pinned when `pinned`
+    bool pinned = false;
     uint64_t n_words = 0;
     std::vector<uint64_t> start;       // n_reads + 1
     uint64_t n_reads = 0;
     int max_len = 0;
+    void alloc(uint64_t words, bool want_pinned) {
+        seq = nullptr; pinned = false;
+        if (want_pinned && cudaHostAlloc((void **)&seq, (words + 64) * 4, cudaHostAllocDefault) == cudaSuccess) {
+            pinned = true;
+            memset(seq, 0, (words + 64) * 4);
+        } else {
+            cudaGetLastError();
+            seq = (uint32_t *)calloc(words + 64, 4);
+        }
+    }
+    void release() {
+        if (pinned) cudaFreeHost(seq); else free(seq);
+        seq = nullptr;
+    }
 };
 
-Reads load_read_lib(const std::string &prefix, int threads) {
+Reads load_read_lib(const std::string &prefix, int threads, bool want_pinned) {
     Reads R;
     long long total_bases = 0, num_reads = 0;
     {
@@ -149,7 +169,7 @@ Reads load_read_lib(const std::string &prefix, int threads) {
         die("read library " + prefix + ": .bin holds " + std::to_string(R.n_reads) + " reads / " + std::to_string(bases) +
             " bases, .lib_info says " + std::to_string(num_reads) + " / " + std::to_string(total_bases));
     R.n_words = bases / 16 + 1;
-    R.seq = (uint32_t *)calloc(R.n_words + 4, 4);
+    R.alloc(R.n_words, want_pinned);
     if (!R.seq) die("out of host memory for the packed reads");
     // pass 2: reverse each read into its bit range; reads are independent except for shared boundary words (atomic OR)
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
@@ -235,11 +255,13 @@ void append_assist(Reads &R, const std::string &file) {
                 extra, n_seq_info, n_bases_info);
     const uint64_t total = R.start.back() + extra;
     const uint64_t new_words = total / 16 + 1;
-    uint32_t *ns = (uint32_t *)calloc(new_words + 4, 4);
+    Reads N2;
+    N2.alloc(new_words, R.pinned);
+    uint32_t *ns = N2.seq;
     if (!ns) die("out of host memory for the assist sequences");
     memcpy(ns, R.seq, R.n_words * 4);
-    free(R.seq);
-    R.seq = ns; R.n_words = new_words;
+    R.release();
+    R.seq = ns; R.pinned = N2.pinned; R.n_words = new_words;
     uint64_t g = R.start.back();
     for (auto &q : seqs) {
         for (size_t i = q.size(); i-- > 0;) {                  // reversed, not complemented
@@ -251,13 +273,15 @@ void append_assist(Reads &R, const std::string &file) {
     R.n_reads += seqs.size();
 }
 
-// ---- SdbgWriter equivalent: one record file per shard (here one), sdbg_info in the reference's exact text format
+// ---- SdbgWriter equivalent (sdbg_multi_io.h:34-199): one record file per GPU (= per lv1-bucket shard; a bucket's
+// records are contiguous in exactly one file, :86-91), one sdbg_info over all of them in the reference's exact text format
 struct Writer {
-    std::string prefix;
+    int file_id = 0;
     FILE *f = nullptr;
     long long offset = 0;
-    std::vector<long long> file_id, start, n_items, n_tips, n_large;
-    Writer() : file_id(MGTA_NUM_BUCKETS, -1), start(MGTA_NUM_BUCKETS, 0), n_items(MGTA_NUM_BUCKETS, 0), n_tips(MGTA_NUM_BUCKETS, 0),
+    int wpt = 0;
+    std::vector<long long> fid, start, n_items, n_tips, n_large;
+    Writer() : fid(MGTA_NUM_BUCKETS, -1), start(MGTA_NUM_BUCKETS, 0), n_items(MGTA_NUM_BUCKETS, 0), n_tips(MGTA_NUM_BUCKETS, 0),
                n_large(MGTA_NUM_BUCKETS, 0) {}
 };
 
@@ -268,14 +292,136 @@ int sink(void *user, int32_t b0, int32_t b1, const void *bytes, uint64_t n_bytes
     for (int b = b0; b < b1; ++b) {
         const int64_t *m = meta + (size_t)(b - b0) * 3;
         w->n_items[b] = m[0]; w->n_tips[b] = m[1]; w->n_large[b] = m[2];
-        if (m[0]) { w->file_id[b] = 0; w->start[b] = off; }
-        off += m[0] * 2 + m[2] * 2;                             // u16 record (+ u16 multiplicity), filled in below with tip words
+        if (m[0]) { w->fid[b] = w->file_id; w->start[b] = off; }
+        off += m[0] * 2 + m[2] * 2 + m[1] * 4LL * w->wpt;       // u16 record (+ u16 multiplicity) (+ tip label words)
     }
-    w->offset += (long long)n_bytes;
+    if (off != w->offset + (long long)n_bytes) return -2;      // the table must add up to the bytes delivered
+    w->offset = off;
     return 0;
 }
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+[[noreturn]] void die_now(const std::string &msg) {            // from a GPU thread: the other threads may sit in a collective
+    fprintf(stderr, "[ERROR] %s\n", msg.c_str());
+    fflush(stderr);
+    _exit(1);
+}
+
+// the collective the library asked for, among the `world` GPU threads of this process, on the context's stream
+void run_collective(const mgta_collective &c, int world, ncclComm_t comm, cudaStream_t st) {
+    ncclResult_t r = ncclSuccess;
+    switch (c.op) {
+        case MGTA_COLL_ALL_TO_ALL:
+            ncclGroupStart();
+            for (int p = 0; p < world && r == ncclSuccess; ++p) {
+                r = ncclSend((const char *)c.send + (size_t)p * c.bytes, c.bytes, ncclChar, p, comm, st);
+                if (r == ncclSuccess) r = ncclRecv((char *)c.recv + (size_t)p * c.bytes, c.bytes, ncclChar, p, comm, st);
+            }
+            ncclGroupEnd();
+            break;
+        case MGTA_COLL_ALL_GATHER: r = ncclAllGather(c.send, c.recv, c.bytes, ncclChar, comm, st); break;
+        case MGTA_COLL_ALL_REDUCE_SUM_U32: r = ncclAllReduce(c.recv, c.recv, c.bytes / 4, ncclUint32, ncclSum, comm, st); break;
+        case MGTA_COLL_ALL_REDUCE_SUM_U64: r = ncclAllReduce(c.recv, c.recv, c.bytes / 8, ncclUint64, ncclSum, comm, st); break;
+        default: die_now("unknown collective requested by the library");
+    }
+    if (r != ncclSuccess) die_now(std::string("NCCL: ") + ncclGetErrorString(r));
+}
+
+struct GpuJob {
+    int g = 0, G = 1;
+    const Options *opt = nullptr;
+    const Reads *R = nullptr;
+    uint64_t n_short = 0;
+    ncclComm_t comm = nullptr;
+    Writer W;
+    std::vector<int64_t> ec;
+    int64_t totals[10] = {0};
+    uint64_t num_mercy = 0;
+    mgta_stage_stats s1, s2;
+    double t_upload = 0, t_s1 = 0, t_s2 = 0;
+};
+
+// one GPU = one lv1-bucket shard = one host thread: upload my slice of the reads, all-gather them over NVLink, then walk
+// the library's protocol for both stages
+void gpu_thread(GpuJob *J) {
+    const Options &opt = *J->opt;
+    const Reads &R = *J->R;
+    const int g = J->g, G = J->G;
+    if (cudaSetDevice(g) != cudaSuccess) die_now("cudaSetDevice(" + std::to_string(g) + ") failed");
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) die_now("cudaStreamCreate failed");
+    mgta_opts mo;
+    memset(&mo, 0, sizeof(mo));
+    mo.kmer_k = opt.kmer_k; mo.min_count = opt.min_count; mo.need_mercy = opt.need_mercy && opt.min_count > 1 ? 1 : 0;
+    mo.device = g; mo.rank = g; mo.world = G;
+    mo.hbm_budget_bytes = (int64_t)opt.gpu_mem;                 // 0 = 90 % of the free HBM, as the reference's "auto detect"
+    mo.stream = st;
+    mgta_ctx *ctx = nullptr;
+    if (mgta_ctx_create(&mo, &ctx) != 0) die_now(std::string("mgta_ctx_create: ") + mgta_last_error(nullptr));
+    auto ck = [&](int rc, const char *what) { if (rc != 0) die_now(std::string(what) + " (GPU " + std::to_string(g) + "): " + mgta_last_error(ctx)); };
+
+    double t = now();
+    if (G == 1) {
+        // pinned host buffers: the upload runs on a copy stream and hides behind the stage-1 extraction
+        ck(mgta_set_reads_async(ctx, R.seq, R.n_words, R.start.data(), R.n_reads, J->n_short, R.max_len), "mgta_set_reads_async");
+    } else {
+        ck(mgta_alloc_reads(ctx, R.n_words, R.n_reads, J->n_short, R.start.back(), R.max_len), "mgta_alloc_reads");
+        void *d_seq, *d_start;
+        uint64_t seq_bytes, start_bytes;
+        ck(mgta_reads_device_buffers(ctx, &d_seq, &seq_bytes, &d_start, &start_bytes), "mgta_reads_device_buffers");
+        // every GPU uploads 1/G of both arrays over its own PCIe link; one group of broadcasts (an all-gather with exact
+        // part sizes) over NVLink completes the buffers everywhere
+        auto part = [&](uint64_t bytes, int r) { return (bytes * (uint64_t)r / G) & ~(uint64_t)15; };
+        for (int pass = 0; pass < 2; ++pass) {
+            const char *src = pass ? (const char *)R.start.data() : (const char *)R.seq;
+            char *dst = pass ? (char *)d_start : (char *)d_seq;
+            const uint64_t bytes = pass ? start_bytes : seq_bytes;
+            const uint64_t lo = part(bytes, g), hi = g + 1 == G ? bytes : part(bytes, g + 1);
+            if (hi > lo && cudaMemcpyAsync(dst + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, st) != cudaSuccess) die_now("H2D of the reads failed");
+            ncclGroupStart();
+            for (int r = 0; r < G; ++r) {
+                const uint64_t a = part(bytes, r), b = r + 1 == G ? bytes : part(bytes, r + 1);
+                if (b > a && ncclBroadcast(dst + a, dst + a, b - a, ncclChar, r, J->comm, st) != ncclSuccess) die_now("ncclBroadcast of the reads failed");
+            }
+            ncclGroupEnd();
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) die_now("read distribution failed");
+    }
+    J->t_upload = now() - t;
+
+    auto run_stage = [&](int stage) {
+        ck(mgta_sharded_begin(ctx, stage, stage == 2 ? sink : nullptr, stage == 2 ? (void *)&J->W : nullptr), "mgta_sharded_begin");
+        for (;;) {
+            mgta_collective c;
+            ck(mgta_sharded_step(ctx, &c), stage == 1 ? "stage 1" : "stage 2");
+            if (c.op == MGTA_COLL_NONE) break;
+            run_collective(c, G, J->comm, st);
+        }
+    };
+    t = now();
+    if (opt.min_count > 1) {
+        run_stage(1);
+        J->ec.assign(MGTA_NUM_BUCKETS, 0);
+        ck(mgta_sharded_result(ctx, J->ec.data(), nullptr), "mgta_sharded_result");
+        if (mo.need_mercy) ck(mgta_get_num_mercy(ctx, &J->num_mercy), "mgta_get_num_mercy");
+    }
+    J->t_s1 = now() - t;
+    t = now();
+    J->W.file_id = g;
+    J->W.wpt = (2 * opt.kmer_k + 31) / 32;
+    const std::string fn = opt.output_prefix + ".sdbg." + std::to_string(g);
+    J->W.f = fopen(fn.c_str(), "wb");
+    if (!J->W.f) die_now("cannot write " + fn);
+    run_stage(2);
+    ck(mgta_sharded_result(ctx, nullptr, J->totals), "mgta_sharded_result");
+    fclose(J->W.f);
+    J->t_s2 = now() - t;
+    mgta_get_stats(ctx, 1, &J->s1);
+    mgta_get_stats(ctx, 2, &J->s2);
+    mgta_ctx_destroy(ctx);
+    cudaStreamDestroy(st);
+}
 
 }  // namespace
 
@@ -283,7 +429,17 @@ int build_graph(int argc, char **argv) {
     const double t0 = now();
     Options opt = parse(argc, argv);
 
-    Reads R = load_read_lib(opt.read_lib_file, opt.num_cpu_threads);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) die("no CUDA device (there is no CPU fallback)");
+    int G = n_dev;                                               // all visible GPUs (CUDA_VISIBLE_DEVICES); MGTA_NUM_GPUS caps it
+    if (const char *e = getenv("MGTA_NUM_GPUS")) G = std::max(1, std::min(n_dev, atoi(e)));
+    G = std::min(G, 16);
+    if (opt.need_mercy && opt.min_count > 1 && G > 1) {
+        fprintf(stderr, "[B200] --need_mercy runs on one GPU: using GPU 0 only\n");
+        G = 1;
+    }
+
+    Reads R = load_read_lib(opt.read_lib_file, opt.num_cpu_threads, G == 1);
     fprintf(stderr, "[B200] %llu reads, %llu bases, max length %d, loaded in %.2f s\n", (unsigned long long)R.n_reads,
             (unsigned long long)R.start.back(), R.max_len, now() - t0);
     if (R.n_reads == 0) die("empty read library");
@@ -294,20 +450,26 @@ int build_graph(int argc, char **argv) {
                 (unsigned long long)R.start.back());
     }
 
-    mgta_opts mo;
-    memset(&mo, 0, sizeof(mo));
-    mo.kmer_k = opt.kmer_k; mo.min_count = opt.min_count; mo.need_mercy = opt.need_mercy && opt.min_count > 1 ? 1 : 0;
-    mo.device = 0; mo.rank = 0; mo.world = 1;
-    mo.hbm_budget_bytes = (int64_t)opt.gpu_mem;                 // 0 = 90 % of the free HBM, as the reference's "auto detect"
-    mgta_ctx *ctx = nullptr;
-    if (mgta_ctx_create(&mo, &ctx) != 0) die(std::string("mgta_ctx_create: ") + mgta_last_error(nullptr));
-    auto ck = [&](int rc, const char *what) { if (rc != 0) die(std::string(what) + ": " + mgta_last_error(ctx)); };
-
+    std::vector<ncclComm_t> comms(G, nullptr);
+    if (G > 1) {
+        std::vector<int> devs(G);
+        for (int g = 0; g < G; ++g) devs[g] = g;
+        ncclResult_t r = ncclCommInitAll(comms.data(), G, devs.data());
+        if (r != ncclSuccess) die(std::string("ncclCommInitAll: ") + ncclGetErrorString(r));
+    }
     const double t1 = now();
-    ck(mgta_set_reads(ctx, R.seq, R.n_words, R.start.data(), R.n_reads, n_short, R.max_len), "mgta_set_reads");
+    std::vector<GpuJob> jobs(G);
+    std::vector<std::thread> threads;
+    for (int g = 0; g < G; ++g) {
+        jobs[g].g = g; jobs[g].G = G; jobs[g].opt = &opt; jobs[g].R = &R; jobs[g].n_short = n_short; jobs[g].comm = comms[g];
+        threads.emplace_back(gpu_thread, &jobs[g]);
+    }
+    for (auto &th : threads) th.join();
+    const double t2 = now();
+    for (auto c : comms) if (c) ncclCommDestroy(c);
+
     if (opt.min_count > 1) {
-        std::vector<int64_t> ec(MGTA_NUM_BUCKETS, 0);
-        ck(mgta_stage1(ctx, ec.data()), "mgta_stage1");
+        const std::vector<int64_t> &ec = jobs[0].ec;                // all-reduced: whole on every GPU
         FILE *cf = fopen((opt.output_prefix + ".counting").c_str(), "w");     // s1.cpp:925-930
         if (!cf) die("cannot write " + opt.output_prefix + ".counting");
         long long acc = 0;
@@ -316,55 +478,38 @@ int build_graph(int argc, char **argv) {
         long long solid = 0;
         for (int i = opt.min_count; i <= 65535; ++i) solid += ec[i];
         fprintf(stderr, "[B200] Total number of solid edges: %lld\n", solid);
-        if (mo.need_mercy) {                                                       // s2.cpp:241 logs the same figure
-            uint64_t nm = 0;
-            ck(mgta_get_num_mercy(ctx, &nm), "mgta_get_num_mercy");
-            fprintf(stderr, "[B200] Number mercy: %llu\n", (unsigned long long)nm);
-        }
+        if (opt.need_mercy) fprintf(stderr, "[B200] Number mercy: %llu\n", (unsigned long long)jobs[0].num_mercy);   // s2.cpp:241
     }
-    Writer W;
-    W.prefix = opt.output_prefix;
-    W.f = fopen((opt.output_prefix + ".sdbg.0").c_str(), "wb");
-    if (!W.f) die("cannot write " + opt.output_prefix + ".sdbg.0");
-    int64_t totals[10];
-    ck(mgta_stage2(ctx, sink, &W, totals), "mgta_stage2");
-    fclose(W.f);
-    const double t2 = now();
 
-    // exact byte offsets of the buckets inside the file (records + tip labels)
+    // sdbg_info over all files (sdbg_multi_io.h:160-187): num_threads = number of files, every row names its file
     const int wpt = (2 * opt.kmer_k + 31) / 32;
-    {
-        long long off = 0;
-        for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) {
-            if (W.n_items[b]) W.start[b] = off;
-            off += W.n_items[b] * 2 + W.n_large[b] * 2 + W.n_tips[b] * 4LL * wpt;
-        }
-        if (off != W.offset) die("internal: bucket table does not add up to the record stream");
-    }
-    FILE *info = fopen((opt.output_prefix + ".sdbg_info").c_str(), "w");       // sdbg_multi_io.h:160-187
+    FILE *info = fopen((opt.output_prefix + ".sdbg_info").c_str(), "w");
     if (!info) die("cannot write " + opt.output_prefix + ".sdbg_info");
     long long te = 0, tt = 0, tl = 0;
-    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) { te += W.n_items[b]; tt += W.n_tips[b]; tl += W.n_large[b]; }
+    for (auto &J : jobs)
+        for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) { te += J.W.n_items[b]; tt += J.W.n_tips[b]; tl += J.W.n_large[b]; }
     fprintf(info, "k %d\n", opt.kmer_k);
     fprintf(info, "words_per_tip_label %d\n", wpt);
     fprintf(info, "num_buckets %d\n", MGTA_NUM_BUCKETS);
-    fprintf(info, "num_threads %d\n", 1);
+    fprintf(info, "num_threads %d\n", G);
     fprintf(info, "total_size %lld\n", te);
     fprintf(info, "num_tips %lld\n", tt);
     fprintf(info, "large_multi %lld\n", tl);
-    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b)
-        fprintf(info, "%d %d %lld %lld %lld %lld\n", b, (int)W.file_id[b], W.start[b], W.n_items[b], W.n_tips[b], W.n_large[b]);
+    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) {
+        const GpuJob *own = nullptr;
+        for (auto &J : jobs) if (J.W.n_items[b]) { if (own) die("internal: bucket " + std::to_string(b) + " emitted by two GPUs"); own = &J; }
+        if (own) fprintf(info, "%d %d %lld %lld %lld %lld\n", b, (int)own->W.fid[b], own->W.start[b], own->W.n_items[b], own->W.n_tips[b], own->W.n_large[b]);
+        else fprintf(info, "%d %d %lld %lld %lld %lld\n", b, -1, 0LL, 0LL, 0LL, 0LL);
+    }
     fclose(info);
 
-    mgta_stage_stats s1, s2;
-    mgta_get_stats(ctx, 1, &s1);
-    mgta_get_stats(ctx, 2, &s2);
-    fprintf(stderr, "[B200] stage 1: %.1f ms device (%llu items), stage 2: %.1f ms device (%llu items, %lld edges); "
-                    "reads-in-host-memory -> files: %.2f s\n", s1.ms_total, (unsigned long long)s1.n_items, s2.ms_total,
-            (unsigned long long)s2.n_items, te, t2 - t1);
+    for (auto &J : jobs)
+        fprintf(stderr, "[B200] GPU %d: reads on the device in %.2f s; stage 1 %.1f ms device (%llu items) / %.2f s wall; stage 2 %.1f ms device "
+                        "(%llu items, %llu edges) / %.2f s wall\n", J.g, J.t_upload, J.s1.ms_total, (unsigned long long)J.s1.n_items, J.t_s1,
+                J.s2.ms_total, (unsigned long long)J.s2.n_items, (unsigned long long)J.s2.n_edges, J.t_s2);
+    fprintf(stderr, "[B200] %d GPU(s): reads-in-host-memory -> files: %.2f s; %lld edges\n", G, t2 - t1, te);
     fprintf(stderr, "Real: %.4f\n", now() - t0);                 // utils.h:124 prints the same line
-    mgta_ctx_destroy(ctx);
-    free(R.seq);
+    R.release();
     return 0;
 }
 

@@ -96,6 +96,7 @@ struct mgta_ctx {
     unsigned long long *d_xs = nullptr;    // scan-sharded exchange: input regions of the level-1 split
     int edge_row_words = 0;
     bool edges_valid = false;
+    bool edges_complete = false;           // d_edges holds the edges of the WHOLE hash space (one shard, or the general counting mode)
     bool solid_valid = false;              // d_solid holds the is_solid vector of the last stage 1 (derived on demand)
     bool stage1_done = false;
     uint32_t *d_hist_s2 = nullptr;
@@ -122,6 +123,20 @@ struct mgta_ctx {
     uint64_t n_tips = 0, tips_cap = 0;
     bool tips_valid = false;
     uint32_t *d_hist_bak = nullptr;        // d_hist_s2 before the node pass added the tip items (restored when the pass restarts)
+    // sharded build (mgta_sharded_*): the protocol state between two collectives
+    struct Sharded {
+        int stage = 0, state = 0, attempt = 0;
+        bool timing = false;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        mgta_bucket_sink sink = nullptr;
+        void *user = nullptr;
+        unsigned long long *d_small = nullptr, *h_small = nullptr;   // world * (world + 2) u64: counts tables
+        uint64_t slab = 0;
+        std::vector<uint64_t> recv_counts;
+        std::vector<int64_t> ec, totals;
+    } sh;
+    // stage 2 over several row segments (the padded all-gather of the shards' edge lists): {first row, rows}
+    std::vector<std::pair<uint64_t, uint64_t>> edge_segs;
 };
 
 // Host waits on the context's stream.  A blocking cudaStreamSynchronize puts the thread to sleep; on a loaded host the
@@ -246,10 +261,11 @@ size_t carve(Plan &pl, uint64_t cap, uint64_t n_dollar) {
     pl.off_list1 = o; o += al((size_t)pl.list_cap * sizeof(Seg));
     pl.off_giants = o; o += al((size_t)pl.giants_cap * sizeof(Giant));
     pl.off_out = o;
-    // stage-2 record stream, guaranteed bound: every record is a run of >= 1 items (2 B), a u16 multiplicity
-    // needs a run of > 254 items, a tip label needs an item with a == $ (counted by the histogram pass)
+    // stage-2 record stream, guaranteed bound: every record is a run of >= 1 items (2 B); the items are WEIGHTED (one
+    // item per distinct edge carrying its multiplicity), so any single item can need the u16 multiplicity (2 B more);
+    // a tip label needs an item with a == $ (n_dollar bounds them)
     const int wpt = (2 * pl.k + 31) / 32;
-    pl.out_cap = pl.stage == 2 ? 2 * cap + 2 * (cap / 255 + 1) + 4ull * wpt * std::min<uint64_t>(cap, n_dollar) + 4096 : 0;
+    pl.out_cap = pl.stage == 2 ? 4 * cap + 4ull * wpt * std::min<uint64_t>(cap, n_dollar) + 4096 : 0;
     o += al(pl.out_cap);
     pl.total = o;
     return o;
@@ -321,6 +337,12 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaHostAlloc(&ctx->h_hist2, ((size_t)1 << ctx->PB) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaMalloc(&ctx->d_xs, (size_t)(MAX_OWNERS + 1) * 24)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if (opts->world > 1) {
+        if (opts->world > MAX_OWNERS) { g_create_error = "at most 16 shards"; delete ctx; return MGTA_ERR_ARG; }
+        const size_t small = (size_t)opts->world * (opts->world + 2) * 8;
+        if ((e = cudaMalloc(&ctx->sh.d_small, small)) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = cudaHostAlloc(&ctx->sh.h_small, small, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    }
     *out = ctx;
     return MGTA_OK;
 }
@@ -334,6 +356,9 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
     cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs); cudaFree(ctx->d_cand); cudaFree(ctx->d_tips); cudaFree(ctx->d_hist_bak);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_hist2);
+    cudaFree(ctx->sh.d_small); cudaFreeHost(ctx->sh.h_small);
+    if (ctx->sh.ev0) cudaEventDestroy(ctx->sh.ev0);
+    if (ctx->sh.ev1) cudaEventDestroy(ctx->sh.ev1);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     for (auto e : ctx->ev_chunk) cudaEventDestroy(e);
@@ -954,6 +979,8 @@ int count_reset_outputs(mgta_ctx *ctx, const CountPlan &cp) {
     } else {
         ctx->n_edges = 0;
         ctx->edges_all_valid = false;
+        ctx->edge_segs.clear();
+        ctx->edges_complete = false;
         ctx->tips_valid = false;
         ctx->n_tips = 0;
         CK(cudaMemsetAsync(ctx->d_hist_s2, 0, ((size_t)1 << ctx->PB) * 4, ctx->stream));
@@ -985,6 +1012,7 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
         if (!cp.mark_mode) {
             if ((rc = count_reset_outputs(ctx, cp))) return rc;
             ctx->edges_valid = true;
+            ctx->edges_complete = mode == CM_GENERAL || ctx->opt.world == 1;
         }
         return MGTA_OK;
     }
@@ -1052,7 +1080,8 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
         }
         if (!retry) break;
     }
-    if (cp.mark_mode) ctx->solid_valid = true; else ctx->edges_valid = true;
+    if (cp.mark_mode) ctx->solid_valid = true;
+    else { ctx->edges_valid = true; ctx->edges_complete = mode == CM_GENERAL || ctx->opt.world == 1; }
     return MGTA_OK;
 }
 
@@ -1685,10 +1714,19 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         memset(&IP, 0, sizeof(IP));
         IP.edges = ctx->edges_all_valid ? ctx->d_edges_all : ctx->d_edges;
         IP.n_edges = ctx->edges_all_valid ? ctx->n_edges_all : ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
+        const bool segmented = ctx->edges_all_valid && !ctx->edge_segs.empty();
         IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = nb1; IP.b1_lo = g1_lo; IP.dst = bufA; IP.cap = pl.cap;
         IP.err = ctx->d_ctr + CTR_ERR;
         if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
-        if (launch_item_part(WE, plus, tips_in, IP, ctx->stream))
+        if (segmented) {                                   // the shards' lists side by side, each padded to the longest
+            for (auto &sg : ctx->edge_segs) {
+                IP.edges = ctx->d_edges_all + sg.first * (size_t)(WE + 1);
+                IP.n_edges = sg.second;
+                if (sg.second && launch_item_part(WE, plus, false, IP, ctx->stream))
+                    FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                st->n_launches++;
+            }
+        } else if (launch_item_part(WE, plus, tips_in, IP, ctx->stream))
             FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         CK(cudaGetLastError());
         if (tips_in && ctx->n_tips) {
@@ -1987,7 +2025,7 @@ extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int
     if (!ctx) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     // several shards: this shard's edge list alone would give a self-consistent but partial graph
-    if (ctx->opt.world > 1 && ctx->edges_valid && !ctx->edges_all_valid)
+    if (ctx->opt.world > 1 && ctx->edges_valid && !ctx->edges_all_valid && !ctx->edges_complete)
         FAIL(MGTA_ERR_STATE, "stage 2 on %d shards needs the solid edges of all shards: exchange them (mgta_edges_reserve) first", ctx->opt.world);
     mgta_stage_stats *st = &ctx->stats[1];
     StageTimer tm;
@@ -2117,6 +2155,7 @@ extern "C" int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t
     CK(mgta_stream_wait(ctx->stream));
     ctx->n_edges_all = n_rows_total;
     ctx->edges_all_valid = true;
+    ctx->edge_segs.clear();
     *dev = ctx->d_edges_all;
     return MGTA_OK;
 }
@@ -2139,3 +2178,5 @@ extern "C" int mgta_get_stats(mgta_ctx *ctx, int stage, mgta_stage_stats *out) {
     *out = ctx->stats[stage - 1];
     return MGTA_OK;
 }
+
+#include "sharded.inc"

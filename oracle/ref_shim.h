@@ -42,5 +42,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #endif
-#define packed /* see header comment */
+/* renamed, not erased: `__attribute__((mgta_ref_not_packed))` is an unknown attribute that g++ ignores (with a warning, -w),
+ * and node_enumerator.h:112-205 uses `packed` as a variable name, which the same renaming keeps valid */
+#define packed mgta_ref_not_packed
 #endif

@@ -4,8 +4,8 @@
         tests/gpu_multi.py [case ...]
 
 One process per GPU over NCCL, exactly the call chain bench.py times: rank 0 uploads the packed reads, ncclBroadcast
-to the other ranks, scan-sharded stage 1 (items all-to-all by hash owner), exchange of the solid-edge rows + stage-2 prefix histogram, bucket-sharded
-stage 2.  The shard streams are concatenated in rank order (= bucket order) on rank 0 and compared with the goldens
+to the other ranks, then mgta_sharded_begin / _step per stage with shards.TorchComm running the collectives the library
+asks for (scan-sharded stage 1: items all-to-all by hash owner; stage 2: exchange of the solid edges, bucket-sharded emission).  The shard streams are concatenated in rank order (= bucket order) on rank 0 and compared with the goldens
 the UNMODIFIED reference binary produced (tests/golden/golden.json): stream hash, per-bucket table hash, w totals and
 the .counting text."""
 import hashlib
@@ -60,15 +60,9 @@ def main():
             (sp, sb), (tp, tb) = ctx.reads_device_buffers()
             dist.broadcast(torch.as_tensor(shards.DevBuf(sp, sb), device=dev), 0)
             dist.broadcast(torch.as_tensor(shards.DevBuf(tp, tb), device=dev), 0)
-            ec = torch.zeros(65536, dtype=torch.int64, device=dev)
-            if m > 1:
-                if os.environ.get("MGTA_REPLICATED_SCAN"):   # legacy: every shard scans all reads for its hash range
-                    ec = torch.from_numpy(ctx.stage1()).to(dev)
-                else:                                        # scan-sharded: scan my reads, all-to-all the items, count
-                    ec = torch.from_numpy(shards.stage1_scan_sharded(ctx, n_reads, rank, world, dist, dev)).to(dev)
-                shards.exchange_ctx(ctx, rank, world, dist, dev)
-                dist.all_reduce(ec)
-            st, meta, totals = ctx.stage2()
+            # the library walks the protocol; TorchComm runs the collectives it asks for with NCCL
+            ec_np, (st, meta, totals) = shards.build_sharded(ctx, rank, world, dist, dev)
+            ec = torch.from_numpy(ec_np if ec_np is not None else np.zeros(65536, dtype=np.int64)).to(dev)
             lo, hi = ctx.shard_range()
         # gather on rank 0: streams in rank order, tables and totals summed
         meta_t = torch.from_numpy(meta).to(dev)
@@ -93,6 +87,7 @@ def main():
             if m > 1:
                 txt = O.counting_text(ec.cpu().numpy())
                 ok = ok and hashlib.sha256(txt.encode()).hexdigest()[:16] == g["counting_sha"]
+            # edge_counting came back all-reduced: already whole on every rank
             print("multi-gpu parity %-22s world=%d shard bytes=%s : %s" % (case, world, [int(x) for x in sizes.tolist()],
                                                                            "OK" if ok else "MISMATCH"), flush=True)
             if not ok:
