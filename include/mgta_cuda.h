@@ -125,51 +125,15 @@ int mgta_stage2_histogram(mgta_ctx *ctx, int64_t *hist);
  * (int64[65536], may be NULL; s1.cpp:744-746).  No-op success when min_count == 1. */
 int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting);
 
-/* Exchange step between the stages when world > 1: the device bit vector (one bit per base
- * position, bit start_idx[r]+o <=> edge offset o of read r).  Each bit is set by exactly one shard,
- * so an all-reduce SUM over uint32 words (NCCL) merges the shards.  */
+/* The device bit vector (one bit per base position, bit start_idx[r]+o <=> edge offset o of read r).  With world > 1 and
+ * mgta_stage1 (every shard scanning all reads for its hash range) each bit is set by exactly one shard, so an
+ * all-reduce SUM over uint32 words merges the shards.  Not on the hot path: the sharded build below exchanges items. */
 int mgta_solid_device_buffer(mgta_ctx *ctx, void **dev_ptr, uint64_t *n_bytes);
 
 /* is_solid in the reference's layout (AtomicBitVector, atomic_bit_vector.h:58-60; bit index
  * (max_read_len-k)*read_id + offset, s1.cpp:151,760).  n_bytes >= ceil(n_short*(max_len-k)/8). */
 int mgta_get_is_solid(mgta_ctx *ctx, uint8_t *host, uint64_t n_bytes);
 int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_bytes);
-
-/* Edge-centric exchange step when world > 1 (replaces the is_solid merge on the hot path): stage 1 of shard r
- * counts the canonical (k+1)-mers whose hash falls in r's range and leaves its solid edges as rows
- * {edge words..., multiplicity} on the device.  Every shard needs ALL rows for stage 2:
- *   1. mgta_edges_local() on every shard -> n_r rows;   all-gather the n_r
- *   2. mgta_edges_reserve(total, offset_r) -> one buffer of `total` rows with the local rows at offset_r
- *   3. the caller fills rows [offset_j, offset_j + n_j) from shard j (ncclBroadcast / all-gather over NVLink)
- *   4. all-reduce SUM (as int32 words) over mgta_edge_hist_device_buffer() -- the stage-2 item histogram by key prefix
- * then mgta_stage2() emits this shard's lv1-bucket range.  With world == 1 none of this is needed. */
-int mgta_edges_local(mgta_ctx *ctx, void **dev, uint64_t *n_rows, int32_t *row_words);
-int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t my_offset_rows, void **dev);
-int mgta_edge_hist_device_buffer(mgta_ctx *ctx, void **dev, uint64_t *n_bytes);
-
-/* Scan-sharded stage 1 when world > 1 (the fast path; mgta_stage1 above makes every shard scan ALL reads for its own
- * hash range instead).  Shard r extracts the canonical (k+1)-mers of reads [read_begin, read_end) only -- the shards'
- * ranges partition the read set -- binned by the shard that owns their hash range, into `world` send slabs:
- *   1. mgta_stage1_scan(ctx, read_begin, read_end, slab_items, &needed).  All shards must use the same slab size
- *      (equal-split all-to-all), so the caller agrees on it: slab_items == 0 only reports in *needed the size this
- *      shard would like (take the maximum over the shards); otherwise the scan runs and *needed receives the slab
- *      size it takes to hold everything: *needed > slab_items means a slab overflowed (skewed input) and NO exchange
- *      is pending -- rescan with the maximum of *needed over the shards, which always fits.
- *   2. mgta_stage1_exchange_buffers(): send / recv device buffers of world * slab_bytes bytes each; slab d of `send`
- *      goes to shard d, slab s of `recv` receives from shard s (one equal-split all-to-all: ncclSend/ncclRecv over
- *      NVLink, torch.distributed.all_to_all_single); send_counts[d] = items in slab d (all-to-all these too)
- *   3. mgta_stage1_count(ctx, recv_counts, edge_counting): recv_counts[s] = items shard s sent here; partitions and
- *      counts the received items exactly like mgta_stage1, leaving this shard's solid-edge rows for the edge exchange
- *      below.  edge_counting (may be NULL) is this shard's share: sum it over the shards.
- * Replaces, like mgta_stage1, cx1.run() with the s1 callbacks (build_graph.cpp:100-113). */
-/* Slab size for the equal partition of the reads (shard d scans reads [n_reads*d/world, n_reads*(d+1)/world)): the
- * largest slice's edge offsets / world + 2 %.  Every shard holds all start_idx, so every shard computes the same
- * value and no agreement round is needed.  Cached until the reads change. */
-int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items);
-int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t read_end, uint64_t slab_items, uint64_t *needed);
-int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev, uint64_t *slab_bytes,
-                                 uint64_t *send_counts /* [world] */);
-int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts /* [world] */, int64_t *edge_counting);
 
 /* Mercy edges (opts.need_mercy, min_count > 1, world == 1): mgta_stage1 then also (a) emits the mercy candidates of
  * s1_lv2_output_ (s1.cpp:762-826: packed ((start_idx + kmer_offset) << 2) | flag; the reference spreads them over
@@ -200,10 +164,13 @@ int mgta_get_num_mercy(mgta_ctx *ctx, uint64_t *num_mercy);
  *                  from rank s (ncclSend / ncclRecv in one group; torch.distributed.all_to_all_single)
  *   ALL_GATHER     every rank contributes `bytes` bytes at send == recv + rank * bytes (in place); recv holds world * bytes
  *   ALL_REDUCE_*   in place (send == recv), `bytes` / 4 resp. / 8 elements, operator SUM
- * Stage 1 replaces cx1.run() with the s1 callbacks (build_graph.cpp:100-113): scan-sharded extraction, all-to-all of the
- * (k+1)-mer items by hash owner, counting; edge_counting is all-reduced, every rank gets the whole array.  Stage 2
- * replaces the s2 run (build_graph.cpp:120-132): exchange of the solid edges, then every rank emits its lv1-bucket
- * range to its sink (ascending buckets; ranks in order give the whole graph). */
+ * Stage 1 replaces cx1.run() with the s1 callbacks (build_graph.cpp:100-113): shard r extracts the canonical (k+1)-mers
+ * of ITS 1/world of the reads, binned by the shard that owns their hash range; one all-to-all moves them; every shard
+ * counts what it received and keeps the solid edges of its hash range; edge_counting is all-reduced (every rank gets the
+ * whole array).  Stage 2 replaces the s2 run (build_graph.cpp:120-132) and replicates nothing: the node pass runs over
+ * the k-mers of each shard's hash range (ops all-to-all), the key-prefix histogram is all-reduced, every shard sends the
+ * stage-2 items of its edges and tips to the shard that emits their lv1 bucket (all-to-all), and every rank sorts and
+ * emits its bucket range to its sink (ascending buckets; ranks in order give the whole graph). */
 typedef enum {
     MGTA_COLL_NONE = 0,
     MGTA_COLL_ALL_TO_ALL = 1,

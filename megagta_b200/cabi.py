@@ -48,9 +48,7 @@ SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_
 EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_reads", "mgta_set_reads_async", "mgta_alloc_reads",
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
-           "mgta_stage1_slab_items", "mgta_stage1_scan", "mgta_stage1_exchange_buffers", "mgta_stage1_count",
-           "mgta_get_mercy_candidates", "mgta_get_num_mercy", "mgta_stage2", "mgta_edges_local", "mgta_edges_reserve",
-           "mgta_edge_hist_device_buffer", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
+           "mgta_get_mercy_candidates", "mgta_get_num_mercy", "mgta_stage2", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version", "mgta_sharded_begin", "mgta_sharded_step", "mgta_sharded_result"]
 
 _lib = None
@@ -78,13 +76,6 @@ def load():
         lib.mgta_stage1_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage2_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_stage1.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-        lib.mgta_stage1_slab_items.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
-        lib.mgta_stage1_scan.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
-                                         ctypes.POINTER(ctypes.c_uint64)]
-        lib.mgta_stage1_exchange_buffers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
-                                                     ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
-                                                     ctypes.c_void_p]
-        lib.mgta_stage1_count.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_solid_device_buffer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                                  ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_get_is_solid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
@@ -93,11 +84,6 @@ def load():
                                                   ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_get_num_mercy.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_stage2.argtypes = [ctypes.c_void_p, SINK, ctypes.c_void_p, ctypes.c_void_p]
-        lib.mgta_edges_local.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64),
-                                         ctypes.POINTER(ctypes.c_int32)]
-        lib.mgta_edges_reserve.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
-        lib.mgta_edge_hist_device_buffer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
-                                                     ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_shard_range.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
         lib.mgta_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(StageStats)]
         lib.mgta_sharded_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, SINK, ctypes.c_void_p]
@@ -178,35 +164,6 @@ class Context:
     def stage1(self):
         ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
         self._check(self.lib.mgta_stage1(self.h, _p(ec)), "mgta_stage1")
-        return ec
-
-    def stage1_slab_items(self):
-        """slab size for the equal partition of the reads over the shards; identical on every shard (no collective)"""
-        n = ctypes.c_uint64()
-        self._check(self.lib.mgta_stage1_slab_items(self.h, ctypes.byref(n)), "mgta_stage1_slab_items")
-        return n.value
-
-    def stage1_scan(self, read_begin, read_end, slab_items=0):
-        """scan-sharded stage 1, step 1: items of reads [read_begin, read_end) binned by owner shard into send slabs of
-        slab_items items.  slab_items == 0: only report the slab size this shard would like.  Returns the slab size
-        that holds everything; a value above slab_items means "overflow, nothing pending: rescan with at least this"."""
-        need = ctypes.c_uint64()
-        self._check(self.lib.mgta_stage1_scan(self.h, read_begin, read_end, slab_items, ctypes.byref(need)), "mgta_stage1_scan")
-        return need.value
-
-    def stage1_exchange_buffers(self):
-        """-> (send ptr, recv ptr, bytes per slab, items per send slab [world])"""
-        a, b, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64()
-        counts = np.zeros(self.opts.world, dtype=np.uint64)
-        self._check(self.lib.mgta_stage1_exchange_buffers(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n), _p(counts)),
-                    "mgta_stage1_exchange_buffers")
-        return a.value, b.value, n.value, counts
-
-    def stage1_count(self, recv_counts):
-        """scan-sharded stage 1, step 3: count the received items -> this shard's share of edge_counting"""
-        rc = np.ascontiguousarray(recv_counts, dtype=np.uint64)
-        ec = np.zeros(NUM_BUCKETS, dtype=np.int64)
-        self._check(self.lib.mgta_stage1_count(self.h, _p(rc), _p(ec)), "mgta_stage1_count")
         return ec
 
     def get_is_solid(self):
@@ -301,22 +258,6 @@ class Context:
             if c is None:
                 return self.sharded_result()
             run_collective(c)
-
-    def edges_local(self):
-        """-> (device pointer, rows, u32 words per row) of this shard's solid-edge list"""
-        p, n, w = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_int32()
-        self._check(self.lib.mgta_edges_local(self.h, ctypes.byref(p), ctypes.byref(n), ctypes.byref(w)), "mgta_edges_local")
-        return p.value, n.value, w.value
-
-    def edges_reserve(self, n_total, my_offset):
-        p = ctypes.c_void_p()
-        self._check(self.lib.mgta_edges_reserve(self.h, n_total, my_offset, ctypes.byref(p)), "mgta_edges_reserve")
-        return p.value
-
-    def edge_hist_device_buffer(self):
-        p, n = ctypes.c_void_p(), ctypes.c_uint64()
-        self._check(self.lib.mgta_edge_hist_device_buffer(self.h, ctypes.byref(p), ctypes.byref(n)), "mgta_edge_hist_device_buffer")
-        return p.value, n.value
 
     def shard_range(self):
         a, b = ctypes.c_int32(), ctypes.c_int32()

@@ -54,6 +54,7 @@ struct ExchangeState {
     uint64_t slab_items = 0;
     size_t send_off = 0, recv_off = 0, xbytes = 0;      // arena offsets of the send / receive slabs, bytes of each
     std::vector<uint64_t> send_counts;
+    unsigned round = 0, n_rounds = 1;
 };
 }  // namespace
 
@@ -71,7 +72,7 @@ struct mgta_ctx {
     uint32_t *d_solid = nullptr;
     uint64_t solid_words = 0;
     // small device state
-    unsigned long long *d_hist = nullptr, *d_cursor = nullptr, *d_meta = nullptr, *d_totals = nullptr, *d_ec = nullptr;
+    unsigned long long *d_hist = nullptr, *d_cursor = nullptr, *d_meta = nullptr, *d_totals = nullptr, *d_ec = nullptr, *d_ec_bak = nullptr;
     unsigned *d_ctr = nullptr;
     unsigned long long *h_pin = nullptr;   // pinned: hist / cursor staging [2 * 65536] + misc [64]
     unsigned char *h_out = nullptr;        // pinned output staging
@@ -90,9 +91,14 @@ struct mgta_ctx {
     // stage-2 items they generate by PB-bit key prefix
     uint32_t *d_edges = nullptr;
     uint64_t n_edges = 0, edges_cap = 0;
-    uint32_t *d_edges_all = nullptr;       // world > 1: the rows of all shards (mgta_edges_reserve); kept across steps
-    uint64_t n_edges_all = 0, edges_all_cap = 0;
-    bool edges_all_valid = false;
+    // world > 1: the stage-2 items this shard received from all shards (sharded.inc): `world` slabs of slab_items items at
+    // the start of the arena, counts per source; valid until the edges change
+    struct ItemSlabs {
+        bool valid = false;
+        uint64_t slab_items = 0, n_dollar = 0;
+        size_t bytes = 0;
+        std::vector<uint64_t> counts;
+    } s2x;
     unsigned long long *d_xs = nullptr;    // scan-sharded exchange: input regions of the level-1 split
     int edge_row_words = 0;
     bool edges_valid = false;
@@ -131,12 +137,12 @@ struct mgta_ctx {
         mgta_bucket_sink sink = nullptr;
         void *user = nullptr;
         unsigned long long *d_small = nullptr, *h_small = nullptr;   // world * (world + 2) u64: counts tables
-        uint64_t slab = 0;
-        std::vector<uint64_t> recv_counts;
+        uint64_t slab = 0, n_ops_all = 0;
+        unsigned round = 0, n_rounds = 1;                      // stage-1 exchange rounds (HBM-limited inputs)
+        std::vector<uint64_t> recv_counts, expect;
+        std::vector<unsigned> bnd;                              // first lv1 bucket of every shard (world + 1 entries)
         std::vector<int64_t> ec, totals;
     } sh;
-    // stage 2 over several row segments (the padded all-gather of the shards' edge lists): {first row, rows}
-    std::vector<std::pair<uint64_t, uint64_t>> edge_segs;
 };
 
 // Host waits on the context's stream.  A blocking cudaStreamSynchronize puts the thread to sleep; on a loaded host the
@@ -315,6 +321,7 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_meta, NUM_BUCKETS * 3 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_totals, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ec, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_ec_bak, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ctr, CTR_COUNT * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     // stage-2 prefix tiles: 2^19 for one GPU; the item count grows with the shards (weak scaling), so each doubling of the
     // world adds a prefix bit and the tiles keep their size (measured at 8 GPUs with 2^20 tiles: every tile overflows
@@ -330,10 +337,10 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     }
     if ((e = cudaMalloc(&ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_hist_bak, ((size_t)1 << ctx->PB) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
-    // one shard: stage 2 takes its $-items from the node pass (a third of the items to partition and sort); several
-    // shards still exchange whole edge lists and generate every item (MGTA_NODE_PASS=0/1 overrides, A/B switch)
-    ctx->node_pass = opts->world == 1;
-    if (const char *e3 = getenv("MGTA_NODE_PASS")) ctx->node_pass = atoi(e3) != 0 && opts->world == 1;
+    // stage 2 takes its $-items from the node pass (a third of the items to partition and sort).  MGTA_NODE_PASS=0: every
+    // edge generates all six items and the group logic drops the covered $-items (one shard only; A/B switch)
+    ctx->node_pass = true;
+    if (const char *e3 = getenv("MGTA_NODE_PASS")) ctx->node_pass = atoi(e3) != 0 || opts->world > 1;
     if ((e = cudaHostAlloc(&ctx->h_hist2, ((size_t)1 << ctx->PB) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaMalloc(&ctx->d_xs, (size_t)(MAX_OWNERS + 1) * 24)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
@@ -352,9 +359,9 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     cudaSetDevice(ctx->opt.device);
     mgta_stream_wait(ctx->stream);
     cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec); cudaFree(ctx->d_ec_bak);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
-    cudaFree(ctx->d_edges_all); cudaFree(ctx->d_xs); cudaFree(ctx->d_cand); cudaFree(ctx->d_tips); cudaFree(ctx->d_hist_bak);
+    cudaFree(ctx->d_xs); cudaFree(ctx->d_cand); cudaFree(ctx->d_tips); cudaFree(ctx->d_hist_bak);
     cudaFreeHost(ctx->h_pin); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_hist2);
     cudaFree(ctx->sh.d_small); cudaFreeHost(ctx->sh.h_small);
     if (ctx->sh.ev0) cudaEventDestroy(ctx->sh.ev0);
@@ -402,7 +409,7 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     ctx->n_words = n_words; ctx->n_reads = n_reads; ctx->n_short = n_short; ctx->total_bases = total;
     ctx->max_len = max_len;
     ctx->edges_valid = false;
-    ctx->edges_all_valid = false;
+    ctx->s2x.valid = false;
     ctx->solid_valid = false;
     ctx->stage1_done = false;
     ctx->n_positions_valid = false;
@@ -533,21 +540,22 @@ int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     return MGTA_OK;
 }
 
-// shard = contiguous bucket range balanced by item count, from ctx->hist
+// shard = contiguous bucket range balanced by item count, from ctx->hist: first bucket of shard r
+int shard_boundary(const mgta_ctx *ctx, uint64_t total, int r) {
+    if (r <= 0) return 0;
+    if (r >= ctx->opt.world) return (int)NUM_BUCKETS;
+    const long double target = (long double)total * r / ctx->opt.world;
+    uint64_t acc = 0;
+    for (int b = 0; b < NUM_BUCKETS; ++b) {
+        if ((long double)acc >= target) return b;
+        acc += (uint64_t)ctx->hist[b];
+    }
+    return (int)NUM_BUCKETS;
+}
+
 void set_shard_range(mgta_ctx *ctx, uint64_t total) {
-    auto boundary = [&](int r) {
-        if (r <= 0) return 0;
-        if (r >= ctx->opt.world) return (int)NUM_BUCKETS;
-        const long double target = (long double)total * r / ctx->opt.world;
-        uint64_t acc = 0;
-        for (int b = 0; b < NUM_BUCKETS; ++b) {
-            if ((long double)acc >= target) return b;
-            acc += (uint64_t)ctx->hist[b];
-        }
-        return (int)NUM_BUCKETS;
-    };
-    ctx->shard_lo = boundary(ctx->opt.rank);
-    ctx->shard_hi = boundary(ctx->opt.rank + 1);
+    ctx->shard_lo = shard_boundary(ctx, total, ctx->opt.rank);
+    ctx->shard_hi = shard_boundary(ctx, total, ctx->opt.rank + 1);
 }
 
 int finish_timing(mgta_ctx *ctx, mgta_stage_stats *st) {
@@ -978,8 +986,7 @@ int count_reset_outputs(mgta_ctx *ctx, const CountPlan &cp) {
         CK(cudaMemsetAsync(ctx->d_solid, 0, ctx->solid_words * 4, ctx->stream));
     } else {
         ctx->n_edges = 0;
-        ctx->edges_all_valid = false;
-        ctx->edge_segs.clear();
+        ctx->s2x.valid = false;
         ctx->edges_complete = false;
         ctx->tips_valid = false;
         ctx->n_tips = 0;
@@ -1086,7 +1093,11 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
 }
 
 // ---- scan-sharded stage 1 (world > 1): scan, [caller: all-to-all], count ---------------------------------------------
-int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab_in, uint64_t *needed, mgta_stage_stats *st) {
+// round / n_rounds: the hash range of every shard is cut into n_rounds slices of level-1 bins and one exchange handles
+// one slice (scan of the same reads again, 1 / n_rounds of the items): for inputs whose items do not fit the HBM at once.
+// dry_run: only compute the arena bytes this exchange would need (*needed), nothing is launched.
+int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab_in, uint64_t *needed, mgta_stage_stats *st,
+                  unsigned round = 0, unsigned n_rounds = 1, bool dry_run = false) {
     ExchangeState &X = ctx->xch;
     X.valid = false;
     if (r_begin > r_end || r_end > ctx->n_reads) FAIL(MGTA_ERR_ARG, "stage1_scan: bad read range");
@@ -1097,6 +1108,21 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
     int rc = make_count_plan(ctx, CM_STAGE1, cp);
     if (rc) return rc;
     st->key_words = cp.WE; st->item_words = cp.IW; st->sort_cap = (int)cp.tab_cap;
+    {                                                              // this round's slice of my level-1 bins
+        const unsigned lo = cp.r_lo, cnt = cp.r_hi - cp.r_lo;
+        cp.r_lo = lo + (unsigned)((uint64_t)cnt * round / n_rounds);
+        cp.r_hi = lo + (unsigned)((uint64_t)cnt * (round + 1) / n_rounds);
+    }
+    if (dry_run) {
+        const uint64_t slab_items = (slab_in + 31) & ~(uint64_t)31;
+        const size_t xbytes = (size_t)world * cp.IW * slab_items * 4;
+        unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
+        if (cp.r_hi <= cp.r_lo) n_batches = 1;
+        CountLay L;
+        count_layout(cp, L, n_batches, 1.15, xbytes, xbytes, (uint64_t)world * slab_items);
+        *needed = L.total;
+        return MGTA_OK;
+    }
     ctx->edges_valid = false;
     ctx->edge_row_words = cp.WE + 1;
     // edge offsets of the local reads, base range of the scan
@@ -1148,6 +1174,7 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
             EP.dst = send; EP.cap = slab_items; EP.err = ctx->d_ctr + CTR_ERR;
             EP.n_owner = world;
             for (int d = 0; d <= world; ++d) EP.owner_lo[d] = owner_lo[d];
+            EP.n_rounds = n_rounds; EP.round = round;
             EP.g_begin = g_begin & ~(uint64_t)1023; EP.g_end = g_end; EP.r_begin = r_begin;
             if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
             if (launch_edge_part(cp.WE, cp.PW, EP, g_end - EP.g_begin, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_edge_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1167,6 +1194,7 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
         if (dev_err & ERR_SLAB_OVERFLOW) { st->n_giants++; return MGTA_OK; }         // *needed > slab: the caller rescans
         if (dev_err & ~(unsigned)ERR_SLAB_OVERFLOW) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage1_scan)", dev_err);
         X.cp = cp; X.slab_items = slab_items; X.send_off = L.A; X.recv_off = L.R; X.xbytes = xbytes;
+        X.round = round; X.n_rounds = n_rounds;
         X.valid = true;
         return MGTA_OK;
     }
@@ -1185,7 +1213,7 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
                                                 (unsigned long long)recv_counts[s], (unsigned long long)X.slab_items);
         n_recv += recv_counts[s];
     }
-    if ((rc = count_reset_outputs(ctx, cp))) return rc;
+    if (X.round == 0 && (rc = count_reset_outputs(ctx, cp))) return rc;         // later rounds add to what the earlier ones left
     if (n_recv == 0 || cp.r_lo >= cp.r_hi) { ctx->edges_valid = true; return MGTA_OK; }
     // input regions of the level-1 split = the slabs received from the shards
     std::vector<unsigned long long> in_start(world + 1, 0), in_count(world + 1, 0);
@@ -1196,16 +1224,24 @@ int exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats 
         chunk_pref[s + 1] = chunk_pref[s] + (unsigned)((recv_counts[s] + cp.T - 1) / cp.T);
     }
     unsigned long long *d_xs = ctx->d_xs;                          // [in_start | in_count | chunk_pref]: 3 small arrays
-    cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    CK(cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     const size_t budget = hbm_budget(ctx);
+    // state a restart of this round must go back to (a level-1 slab overflow is detected after earlier batches counted)
+    const uint64_t edges0 = ctx->n_edges;
+    CK(cudaMemcpyAsync(ctx->d_hist_bak, ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ec_bak, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     double slack = 1.15;
     for (int attempt = 0;; ++attempt) {
         bool retry = false;
         const uint64_t giants0 = st->n_giants;
-        st->n_items = 0; st->n_batches = 0;
-        if ((rc = count_reset_outputs(ctx, cp))) return rc;
+        if (X.round == 0) { st->n_items = 0; st->n_batches = 0; }
+        if (attempt) {
+            ctx->n_edges = edges0;
+            CK(cudaMemcpyAsync(ctx->d_hist_s2, ctx->d_hist_bak, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_ec, ctx->d_ec_bak, NUM_BUCKETS * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         CountLay L;
         unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
         count_layout(cp, L, n_batches, slack, X.xbytes, X.xbytes, (uint64_t)world * X.slab_items);
@@ -1447,20 +1483,29 @@ int ensure_solid(mgta_ctx *ctx) {
 // ---- the node pass of stage 2 (node_kernels.cuh) ----------------------------------------------------------
 // {(canonical edge, multiplicity)} -> 2 ops per edge keyed by canonical k-mer -> two hash partition levels -> per-tile
 // tables of (out, in) weights -> the $-items of the tip k-mers (ctx->d_tips) + their share of the stage-2 histogram.
-int run_nodes(mgta_ctx *ctx, mgta_stage_stats *st) {
-    const int k = ctx->opt.kmer_k, KW = kmer_words(k), WE = edge_words(k), W2 = key_words_s2(k), IW = KW + 1;
-    const bool eplus = WE > KW, plus2 = W2 > KW;
-    int rc;
-    ctx->tips_valid = false;
-    ctx->n_tips = 0;
-    const uint64_t n_edges = ctx->n_edges, n_ops = 2 * n_edges;
-    st->n_node_ops = n_ops;
-    st->n_tip_items = 0;
-    if (n_edges == 0) { ctx->tips_valid = true; return MGTA_OK; }
-    CountPlan cp;
+// One shard: run_nodes().  Several: node_exchange_scan() bins the ops of this shard's edges by the shard that owns the
+// k-mer's hash range, one all-to-all moves them, node_exchange_count() finishes like the one-shard pass.
+struct NodeShape {
+    int k, KW, WE, W2, IW;
+    bool eplus, plus2;
+    size_t smem_count, smem_big, row;
+};
+
+NodeShape node_shape(int k) {
+    NodeShape n;
+    n.k = k; n.KW = kmer_words(k); n.WE = edge_words(k); n.W2 = key_words_s2(k); n.IW = n.KW + 1;
+    n.eplus = n.WE > n.KW; n.plus2 = n.W2 > n.KW;
+    n.smem_count = n.smem_big = 0;
+    n.row = (size_t)(n.W2 + 1) * 4;
+    return n;
+}
+
+// n_ops: ops of ALL shards (2 per distinct solid edge); every shard derives the same plan from it
+void make_node_plan(mgta_ctx *ctx, uint64_t n_ops, CountPlan &cp, NodeShape &ns) {
+    ns = node_shape(ctx->opt.kmer_k);
     memset(&cp, 0, sizeof(cp));
-    cp.k = k; cp.WE = KW; cp.PW = 1; cp.IW = IW; cp.has_assist = true; cp.stage1_mode = true; cp.n_pos = n_ops;
-    const size_t slot_bytes = 4 * (size_t)(3 + KW) + 2;
+    cp.k = ns.k; cp.WE = ns.KW; cp.PW = 1; cp.IW = ns.IW; cp.has_assist = true; cp.stage1_mode = true; cp.n_pos = n_ops;
+    const size_t slot_bytes = 4 * (size_t)(3 + ns.KW) + 2;
     cp.tab_cap = 4096; cp.big_cap = 16384;
     while (cp.tab_cap > 1024 && cp.tab_cap * slot_bytes > 106 * 1024) cp.tab_cap >>= 1;
     while (cp.big_cap > cp.tab_cap && cp.big_cap * slot_bytes > 200 * 1024) cp.big_cap >>= 1;
@@ -1472,107 +1517,268 @@ int run_nodes(mgta_ctx *ctx, mgta_stage_stats *st) {
     cp.lb2 = (unsigned)std::min(10, bits / 2);
     cp.lb1 = (unsigned)bits - cp.lb2;
     cp.B1 = 1u << cp.lb1;
-    cp.T = split_chunk_items(IW);
-    cp.r_lo = 0; cp.r_hi = cp.B1;
-    const size_t smem_count = count_smem_bytes(KW, cp.tab_cap, 1), smem_big = count_smem_bytes(KW, cp.big_cap, 1);
+    cp.T = split_chunk_items(ns.IW);
+    cp.r_lo = (unsigned)((uint64_t)cp.B1 * ctx->opt.rank / ctx->opt.world);
+    cp.r_hi = (unsigned)((uint64_t)cp.B1 * (ctx->opt.rank + 1) / ctx->opt.world);
+    ns.smem_count = count_smem_bytes(ns.KW, cp.tab_cap, 1);
+    ns.smem_big = count_smem_bytes(ns.KW, cp.big_cap, 1);
+}
+
+enum { NODE_OK = 0, NODE_RETRY_SLACK = 1, NODE_RETRY_TIPS = 2 };
+
+// One batch of level-1 bins [b_lo, b_hi) whose slabs (buffer A, cursors cur1) and tile histogram hist2 are filled: exact
+// tile offsets, level-2 split, per-tile (out, in) tables, tips.  verdict: NODE_OK, or what the caller must enlarge.
+int node_batch_tail(mgta_ctx *ctx, const CountPlan &cp, const NodeShape &ns, const CountLay &L, unsigned b_lo, unsigned b_hi,
+                    unsigned n_batches, unsigned batch, mgta_stage_stats *st, int &verdict, double &slack, uint64_t &tips_cap) {
+    int rc;
+    verdict = NODE_OK;
+    uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
+    uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+    unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+    unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
+    ScanParams SP;
+    memset(&SP, 0, sizeof(SP));
+    const unsigned NTb = (b_hi - b_lo) << cp.lb2;
+    SP.hist = hist2; SP.NT = NTb; SP.lb2 = cp.lb2; SP.t_lo = 0; SP.t_hi = NTb;
+    SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
+    SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
+    SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
+    SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
+    SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
+    SP.T = cp.T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
+    SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
+    if ((rc = launch_scans(ctx, SP))) return rc;
+    SplitParams XP;
+    memset(&XP, 0, sizeof(XP));
+    XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = ns.IW; XP.WE = ns.KW; XP.mode = 0;
+    XP.sh2 = 32 - cp.bits; XP.lb2 = cp.lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
+    XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
+    if ((rc = launch_split(ctx, XP))) return rc;
+    NodeCountParams CP;
+    memset(&CP, 0, sizeof(CP));
+    CP.src = bufB; CP.cap = L.capB; CP.k = ns.k; CP.off2 = off2; CP.t_lo = 0; CP.t_hi = NTb; CP.ticket = ctx->d_ctr + CTR_TICKET2;
+    CP.tab_cap = cp.tab_cap; CP.tab_limit = cp.tab_limit; CP.tips_out = ctx->d_tips; CP.n_tips = ctx->d_totals + 11;
+    CP.tips_cap = ctx->tips_cap; CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
+    CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = L.NT;
+    CP.err = ctx->d_ctr + CTR_ERR;
+    if (launch_node_count(ns.KW, ns.plus2, CP, (unsigned)(ctx->sm_count * 2), ns.smem_count, ctx->stream))
+        FAIL(MGTA_ERR_CUDA, "k_node_count launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    NodeCountParams CB = CP;                                                     // overflow tiles: one CTA per SM, large table
+    CB.tile_list = CP.ovf_list; CB.n_tile_list = CP.n_ovf; CB.ticket = ctx->d_ctr + CTR_TICKET3;
+    CB.tab_cap = cp.big_cap; CB.tab_limit = cp.big_cap - 1024; CB.ovf_cap = 0; CB.n_ovf = ctx->d_ctr + CTR_NOVF2;
+    if (launch_node_count(ns.KW, ns.plus2, CB, (unsigned)ctx->sm_count, ns.smem_big, ctx->stream))
+        FAIL(MGTA_ERR_CUDA, "k_node_count (overflow pass) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(cudaGetLastError());
+    st->n_launches += 6;
+    unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+    unsigned long long *h_nt = ctx->h_pin + 2 * NUM_BUCKETS + 8;
+    CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_nt, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
+    const unsigned dev_err = h_ctr[CTR_ERR];
+    if (dev_err & ERR_SLAB_OVERFLOW) {
+        std::vector<unsigned long long> hc(b_hi - b_lo);
+        CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long mx = 0;
+        for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
+        slack = std::max(slack * 1.5, (double)mx / ((double)cp.n_pos / cp.B1) * 1.05);
+        verdict = NODE_RETRY_SLACK;
+        return MGTA_OK;
+    }
+    if (dev_err & ERR_EDGE_LIST_FULL) {                             // the tip list was too small: the counter kept counting
+        tips_cap = std::max<uint64_t>(2 * ctx->tips_cap, (uint64_t)((double)h_nt[0] * n_batches / (batch + 1) * 1.1) + 1024);
+        verdict = NODE_RETRY_TIPS;
+        return MGTA_OK;
+    }
+    if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (node pass, bins [%u,%u))", dev_err, b_lo, b_hi);
+    ctx->n_tips = h_nt[0];
+    return MGTA_OK;
+}
+
+int node_ensure_tips(mgta_ctx *ctx, uint64_t tips_cap, size_t row) {
+    if (tips_cap > ctx->tips_cap || !ctx->d_tips) {
+        CK(mgta_stream_wait(ctx->stream));
+        cudaFree(ctx->d_tips);
+        ctx->d_tips = nullptr; ctx->tips_cap = 0;
+        CK(cudaMalloc(&ctx->d_tips, tips_cap * row));
+        ctx->tips_cap = tips_cap;
+    }
+    return MGTA_OK;
+}
+
+int run_nodes(mgta_ctx *ctx, mgta_stage_stats *st) {
+    int rc;
+    ctx->tips_valid = false;
+    ctx->n_tips = 0;
+    const uint64_t n_edges = ctx->n_edges, n_ops = 2 * n_edges;
+    st->n_node_ops = n_ops;
+    st->n_tip_items = 0;
+    if (n_edges == 0) { ctx->tips_valid = true; return MGTA_OK; }
+    CountPlan cp;
+    NodeShape ns;
+    make_node_plan(ctx, n_ops, cp, ns);
+    cp.r_lo = 0; cp.r_hi = cp.B1;                                   // the edge list is complete: this shard sees every k-mer
     const size_t budget = hbm_budget(ctx);
-    const size_t row = (size_t)(W2 + 1) * 4;
     CK(cudaMemcpyAsync(ctx->d_hist_bak, ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     uint64_t tips_cap = std::max<uint64_t>(ctx->tips_cap, std::max<uint64_t>(1u << 20, n_edges / 4));
     double slack = 1.15;
     for (int attempt = 0;; ++attempt) {
         if (attempt >= 10) FAIL(MGTA_ERR_MEM, "node pass: the partition does not settle");
         if (attempt) CK(cudaMemcpyAsync(ctx->d_hist_s2, ctx->d_hist_bak, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (tips_cap > ctx->tips_cap || !ctx->d_tips) {
-            CK(mgta_stream_wait(ctx->stream));
-            cudaFree(ctx->d_tips);
-            ctx->d_tips = nullptr; ctx->tips_cap = 0;
-            CK(cudaMalloc(&ctx->d_tips, tips_cap * row));
-            ctx->tips_cap = tips_cap;
-        }
+        if ((rc = node_ensure_tips(ctx, tips_cap, ns.row))) return rc;
         CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));                  // tip rows (free after the mercy pass of stage 1)
-        bool retry = false;
+        int verdict = NODE_OK;
         CountLay L;
         unsigned n_batches = (cp.B1 + MAX_BINS - 1) / MAX_BINS;
         count_layout(cp, L, n_batches, slack, 0, 0, 0);
         while (L.total > budget && L.bins > 1) { n_batches *= 2; count_layout(cp, L, n_batches, slack, 0, 0, 0); }
         if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 bin of the node pass (%zu B)", budget, L.total);
         if ((rc = ensure_arena(ctx, L.total))) return rc;
-        uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
-        uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
-        unsigned long long *cur1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
-        unsigned long long *off2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.off2);
-        for (unsigned batch = 0; batch < n_batches && !retry; ++batch) {
+        for (unsigned batch = 0; batch < n_batches && verdict == NODE_OK; ++batch) {
             const unsigned b_lo = batch * L.bins, b_hi = std::min(cp.B1, b_lo + L.bins);
             if (b_lo >= b_hi) break;
             if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) return rc;
             if ((rc = begin_timed(ctx, PH_NODES))) return rc;
             NodePartParams NP;
             memset(&NP, 0, sizeof(NP));
-            NP.edges = ctx->d_edges; NP.n_edges = n_edges; NP.k = k; NP.sh1 = 32 - (int)cp.lb1; NP.sh2 = 32 - cp.bits; NP.lb2 = cp.lb2;
-            NP.b_lo = b_lo; NP.b_hi = b_hi; NP.cursor1 = cur1; NP.slab_cap = L.slab_cap; NP.hist2 = hist2; NP.dst = bufA; NP.cap = L.capA;
+            NP.edges = ctx->d_edges; NP.n_edges = n_edges; NP.k = ns.k; NP.sh1 = 32 - (int)cp.lb1; NP.sh2 = 32 - cp.bits; NP.lb2 = cp.lb2;
+            NP.b_lo = b_lo; NP.b_hi = b_hi; NP.cursor1 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1); NP.slab_cap = L.slab_cap;
+            NP.hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2); NP.dst = reinterpret_cast<uint32_t *>(ctx->arena + L.A); NP.cap = L.capA;
             NP.err = ctx->d_ctr + CTR_ERR;
-            if (launch_node_part(KW, eplus, NP, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_node_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (launch_node_part(ns.KW, ns.eplus, NP, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_node_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             CK(cudaGetLastError());
-            ScanParams SP;
-            memset(&SP, 0, sizeof(SP));
-            const unsigned NTb = (b_hi - b_lo) << cp.lb2;
-            SP.hist = hist2; SP.NT = NTb; SP.lb2 = cp.lb2; SP.t_lo = 0; SP.t_hi = NTb;
-            SP.loc = reinterpret_cast<uint32_t *>(ctx->arena + L.loc);
-            SP.tot = reinterpret_cast<unsigned long long *>(ctx->arena + L.tot);
-            SP.base = reinterpret_cast<unsigned long long *>(ctx->arena + L.base);
-            SP.off2 = off2; SP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur2);
-            SP.cursor1 = nullptr; SP.chunk_pref = reinterpret_cast<unsigned *>(ctx->arena + L.chunk_pref);
-            SP.T = cp.T; SP.slab_cap = L.slab_cap; SP.b1_lo = 0;
-            SP.in_start = reinterpret_cast<unsigned long long *>(ctx->arena + L.in_start);
-            if ((rc = launch_scans(ctx, SP))) return rc;
+            st->n_launches++;
+            if ((rc = node_batch_tail(ctx, cp, ns, L, b_lo, b_hi, n_batches, batch, st, verdict, slack, tips_cap))) return rc;
+            if ((rc = end_timed(ctx))) return rc;
+        }
+        if (verdict == NODE_OK) break;
+    }
+    st->n_tip_items = ctx->n_tips;
+    ctx->tips_valid = true;
+    return MGTA_OK;
+}
+
+// ---- sharded node pass: scan (ops of my edges binned by owner), [caller: all-to-all], count ---------------------------
+int node_exchange_scan(mgta_ctx *ctx, uint64_t n_ops_all, uint64_t slab_in, uint64_t *needed, mgta_stage_stats *st) {
+    ExchangeState &X = ctx->xch;
+    X.valid = false;
+    const int world = ctx->opt.world;
+    CountPlan cp;
+    NodeShape ns;
+    make_node_plan(ctx, n_ops_all, cp, ns);
+    int rc;
+    const size_t budget = hbm_budget(ctx);
+    const uint64_t slab_items = (slab_in + 31) & ~(uint64_t)31;
+    const size_t xbytes = (size_t)world * ns.IW * slab_items * 4;
+    unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
+    if (cp.r_hi <= cp.r_lo) n_batches = 1;
+    CountLay L;
+    count_layout(cp, L, n_batches, 1.15, xbytes, xbytes, (uint64_t)world * slab_items);
+    if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the node-pass exchange (%zu B)", budget, L.total);
+    if ((rc = ensure_arena(ctx, L.total))) return rc;
+    uint32_t *send = reinterpret_cast<uint32_t *>(ctx->arena + L.A);
+    unsigned long long *cur = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+    const unsigned long long stride = (unsigned long long)ns.IW * slab_items;
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+    k_init_slab_cursors<<<1, 256, 0, ctx->stream>>>(cur, (unsigned)world, stride);
+    CK(cudaGetLastError());
+    if (ctx->n_edges) {
+        NodePartParams NP;
+        memset(&NP, 0, sizeof(NP));
+        NP.edges = ctx->d_edges; NP.n_edges = ctx->n_edges; NP.k = ns.k; NP.sh1 = 32 - (int)cp.lb1; NP.sh2 = 32 - cp.bits; NP.lb2 = cp.lb2;
+        NP.b_lo = 0; NP.b_hi = cp.B1; NP.cursor1 = cur; NP.slab_cap = slab_items; NP.slab_stride = stride; NP.hist2 = nullptr;
+        NP.dst = send; NP.cap = slab_items; NP.err = ctx->d_ctr + CTR_ERR; NP.n_owner = world;
+        for (int d = 0; d <= world; ++d) NP.owner_lo[d] = (unsigned)((uint64_t)cp.B1 * d / world);
+        if ((rc = begin_timed(ctx, PH_NODES))) return rc;
+        if (launch_node_part(ns.KW, ns.eplus, NP, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_node_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CK(cudaGetLastError());
+        if ((rc = end_timed(ctx))) return rc;
+        st->n_launches++;
+    }
+    unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+    CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
+    X.send_counts.assign(world, 0);
+    uint64_t mx = 0;
+    for (int d = 0; d < world; ++d) { X.send_counts[d] = ctx->h_pin[d] - (unsigned long long)d * stride; mx = std::max(mx, X.send_counts[d]); }
+    const unsigned dev_err = h_ctr[CTR_ERR];
+    *needed = std::max<uint64_t>(slab_items, (mx + 31) & ~(uint64_t)31);
+    if (dev_err & ERR_SLAB_OVERFLOW) return MGTA_OK;                 // *needed > slab: the caller rescans
+    if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (node scan)", dev_err);
+    X.cp = cp; X.slab_items = slab_items; X.send_off = L.A; X.recv_off = L.R; X.xbytes = xbytes;
+    X.valid = true;
+    return MGTA_OK;
+}
+
+int node_exchange_count(mgta_ctx *ctx, const uint64_t *recv_counts, mgta_stage_stats *st) {
+    ExchangeState &X = ctx->xch;
+    if (!X.valid) FAIL(MGTA_ERR_STATE, "node count: no exchange pending");
+    X.valid = false;
+    const CountPlan &cp = X.cp;
+    NodeShape ns = node_shape(ctx->opt.kmer_k);
+    ns.smem_count = count_smem_bytes(ns.KW, cp.tab_cap, 1);
+    ns.smem_big = count_smem_bytes(ns.KW, cp.big_cap, 1);
+    const int world = ctx->opt.world;
+    int rc;
+    ctx->tips_valid = false;
+    ctx->n_tips = 0;
+    uint64_t n_recv = 0;
+    for (int s = 0; s < world; ++s) {
+        if (recv_counts[s] > X.slab_items) FAIL(MGTA_ERR_ARG, "node count: shard %d sent %llu ops, a slab holds %llu", s,
+                                                (unsigned long long)recv_counts[s], (unsigned long long)X.slab_items);
+        n_recv += recv_counts[s];
+    }
+    st->n_node_ops = n_recv;
+    if (n_recv == 0 || cp.r_lo >= cp.r_hi) { ctx->tips_valid = true; return MGTA_OK; }
+    std::vector<unsigned long long> in_start(world + 1, 0), in_count(world + 1, 0);
+    std::vector<unsigned> chunk_pref(world + 1, 0);
+    for (int s = 0; s < world; ++s) {
+        in_start[s] = (unsigned long long)s * cp.IW * X.slab_items;
+        in_count[s] = recv_counts[s];
+        chunk_pref[s + 1] = chunk_pref[s] + (unsigned)((recv_counts[s] + cp.T - 1) / cp.T);
+    }
+    unsigned long long *d_xs = ctx->d_xs;
+    CK(cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));                               // the host vectors die with this frame
+    const size_t budget = hbm_budget(ctx);
+    CK(cudaMemcpyAsync(ctx->d_hist_bak, ctx->d_hist_s2, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    uint64_t tips_cap = std::max<uint64_t>(ctx->tips_cap, std::max<uint64_t>(1u << 20, n_recv / 8));
+    double slack = 1.15;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt >= 10) FAIL(MGTA_ERR_MEM, "node pass: the partition does not settle");
+        if (attempt) CK(cudaMemcpyAsync(ctx->d_hist_s2, ctx->d_hist_bak, ((size_t)1 << ctx->PB) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = node_ensure_tips(ctx, tips_cap, ns.row))) return rc;
+        CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));
+        int verdict = NODE_OK;
+        CountLay L;
+        unsigned n_batches = (cp.r_hi - cp.r_lo + MAX_BINS - 1) / MAX_BINS;
+        count_layout(cp, L, n_batches, slack, X.xbytes, X.xbytes, (uint64_t)world * X.slab_items);
+        if (L.R != X.recv_off) FAIL(MGTA_ERR_INTERNAL, "node count: receive buffer moved");
+        if (L.total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the level-1 slabs of the node pass (%zu B)", budget, L.total);
+        if ((rc = ensure_arena_keep(ctx, L.total, X.recv_off + X.xbytes))) return rc;
+        for (unsigned batch = 0; batch < n_batches && verdict == NODE_OK; ++batch) {
+            const unsigned b_lo = cp.r_lo + batch * L.bins, b_hi = std::min(cp.r_hi, b_lo + L.bins);
+            if (b_lo >= b_hi) break;
+            if ((rc = count_batch_begin(ctx, L, b_hi - b_lo))) return rc;
             SplitParams XP;
             memset(&XP, 0, sizeof(XP));
-            XP.src = bufA; XP.dst = bufB; XP.cap_src = L.capA; XP.cap_dst = L.capB; XP.IW = IW; XP.WE = KW; XP.mode = 0;
-            XP.sh2 = 32 - cp.bits; XP.lb2 = cp.lb2; XP.in_start = SP.in_start; XP.in_count = SP.tot; XP.chunk_pref = SP.chunk_pref;
-            XP.B1 = b_hi - b_lo; XP.cursor2 = SP.cursor2; XP.ticket = ctx->d_ctr + CTR_TICKET; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
+            XP.src = reinterpret_cast<uint32_t *>(ctx->arena + L.R); XP.dst = reinterpret_cast<uint32_t *>(ctx->arena + L.A);
+            XP.cap_src = X.slab_items; XP.cap_dst = L.capA; XP.IW = cp.IW; XP.WE = cp.WE; XP.mode = 2;
+            XP.sh1 = 32 - (int)cp.lb1; XP.sh2 = 32 - cp.bits; XP.lb2 = cp.lb2;
+            XP.in_start = d_xs; XP.in_count = d_xs + (world + 1); XP.chunk_pref = reinterpret_cast<unsigned *>(d_xs + 2 * (world + 1));
+            XP.B1 = (unsigned)world; XP.cursor2 = reinterpret_cast<unsigned long long *>(ctx->arena + L.cur1);
+            XP.ticket = ctx->d_ctr + CTR_NLIST0; XP.T = cp.T; XP.err = ctx->d_ctr + CTR_ERR;
+            XP.b_lo = b_lo; XP.b_hi = b_hi; XP.slab_cap = L.slab_cap; XP.hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
+            if ((rc = begin_timed(ctx, PH_NODES))) return rc;
             if ((rc = launch_split(ctx, XP))) return rc;
-            NodeCountParams CP;
-            memset(&CP, 0, sizeof(CP));
-            CP.src = bufB; CP.cap = L.capB; CP.k = k; CP.off2 = off2; CP.t_lo = 0; CP.t_hi = NTb; CP.ticket = ctx->d_ctr + CTR_TICKET2;
-            CP.tab_cap = cp.tab_cap; CP.tab_limit = cp.tab_limit; CP.tips_out = ctx->d_tips; CP.n_tips = ctx->d_totals + 11;
-            CP.tips_cap = ctx->tips_cap; CP.hist_s2 = ctx->d_hist_s2; CP.s2_shift = 32 - ctx->PB;
-            CP.ovf_list = reinterpret_cast<unsigned *>(ctx->arena + L.ovf); CP.n_ovf = ctx->d_ctr + CTR_NOVF; CP.ovf_cap = L.NT;
-            CP.err = ctx->d_ctr + CTR_ERR;
-            if (launch_node_count(KW, plus2, CP, (unsigned)(ctx->sm_count * 2), smem_count, ctx->stream))
-                FAIL(MGTA_ERR_CUDA, "k_node_count launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            NodeCountParams CB = CP;                                                     // overflow tiles: one CTA per SM, large table
-            CB.tile_list = CP.ovf_list; CB.n_tile_list = CP.n_ovf; CB.ticket = ctx->d_ctr + CTR_TICKET3;
-            CB.tab_cap = cp.big_cap; CB.tab_limit = cp.big_cap - 1024; CB.ovf_cap = 0; CB.n_ovf = ctx->d_ctr + CTR_NOVF2;
-            if (launch_node_count(KW, plus2, CB, (unsigned)ctx->sm_count, smem_big, ctx->stream))
-                FAIL(MGTA_ERR_CUDA, "k_node_count (overflow pass) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            CK(cudaGetLastError());
+            st->n_launches++;
+            if ((rc = node_batch_tail(ctx, cp, ns, L, b_lo, b_hi, n_batches, batch, st, verdict, slack, tips_cap))) return rc;
             if ((rc = end_timed(ctx))) return rc;
-            st->n_launches += 7;
-            unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
-            unsigned long long *h_nt = ctx->h_pin + 2 * NUM_BUCKETS + 8;
-            CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(h_nt, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(mgta_stream_wait(ctx->stream));
-            const unsigned dev_err = h_ctr[CTR_ERR];
-            if (dev_err & ERR_SLAB_OVERFLOW) {
-                std::vector<unsigned long long> hc(b_hi - b_lo);
-                CK(cudaMemcpy(hc.data(), cur1, hc.size() * 8, cudaMemcpyDeviceToHost));
-                unsigned long long mx = 0;
-                for (size_t i = 0; i < hc.size(); ++i) mx = std::max(mx, hc[i] - (unsigned long long)i * L.slab_cap);
-                slack = std::max(slack * 1.5, (double)mx / ((double)n_ops / cp.B1) * 1.05);
-                retry = true;
-                break;
-            }
-            if (dev_err & ERR_EDGE_LIST_FULL) {                     // the tip list was too small: the counter kept counting
-                tips_cap = std::max<uint64_t>(2 * ctx->tips_cap, (uint64_t)((double)h_nt[0] * n_batches / (batch + 1) * 1.1) + 1024);
-                retry = true;
-                break;
-            }
-            if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (node pass, bins [%u,%u))", dev_err, b_lo, b_hi);
-            ctx->n_tips = h_nt[0];
         }
-        if (!retry) break;
+        if (verdict == NODE_OK) break;
     }
     st->n_tip_items = ctx->n_tips;
     ctx->tips_valid = true;
@@ -1582,7 +1788,9 @@ int run_nodes(mgta_ctx *ctx, mgta_stage_stats *st) {
 // ---- the emission pipeline -------------------------------------------------------------------------
 // {(canonical edge, multiplicity)} -> stage-2 items (S a | flags, multiplicity) -> two key-prefix partition levels
 // (exact offsets) -> per-window on-chip sort + W/last/tip/multiplicity records (k_sort_emit) -> sink.
-int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, mgta_stage_stats *st) {
+// from_slabs: the items come from the slabs the shards sent each other (ctx->s2x, at the start of the arena, which the
+// buffers below then leave alone) instead of from this shard's own edge and tip lists.
+int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, mgta_stage_stats *st, bool from_slabs = false) {
     const int k = ctx->opt.kmer_k;
     const int WE = edge_words(k);
     const int W = key_words_s2(k), IW = W + 1;
@@ -1621,10 +1829,12 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
 
     const size_t budget = hbm_budget(ctx);
     struct Lay { size_t A, B, flags, win, state, list0, list1, giants, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, out, tmp, total; } L;
-    const bool tips_in = ctx->node_pass && ctx->tips_valid && !ctx->edges_all_valid;   // $-items come from the node pass
+    const bool tips_in = ctx->node_pass && ctx->tips_valid && !from_slabs;             // $-items come from the node pass
+    const size_t arena_base = from_slabs ? ((ctx->s2x.bytes + 255) & ~(size_t)255) : 0;
     auto layout = [&](uint64_t cap) {
-        carve(pl, cap, tips_in ? ctx->n_tips : cap / 3 + 1);
+        carve(pl, cap, from_slabs ? ctx->s2x.n_dollar : (tips_in ? ctx->n_tips : cap / 3 + 1));
         Carver c;
+        c.o = arena_base;
         L.A = c.take((size_t)IW * pl.cap * 4); L.B = c.take((size_t)IW * pl.cap * 4);
         L.flags = c.take((pl.cap / 32 + 64) * 4);
         const uint64_t n_win = pl.cap / pl.C + 2;
@@ -1646,7 +1856,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     }
     if (L.total > budget)
         FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the largest lv1 bucket (%llu items, need %zu B)", budget, (unsigned long long)max_bucket, L.total);
-    if ((rc = ensure_arena(ctx, L.total))) return rc;
+    if ((rc = ensure_arena_keep(ctx, L.total, arena_base))) return rc;
     uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
     uint32_t *flags = reinterpret_cast<uint32_t *>(ctx->arena + L.flags), *win = reinterpret_cast<uint32_t *>(ctx->arena + L.win);
     unsigned long long *state = reinterpret_cast<unsigned long long *>(ctx->arena + L.state);
@@ -1709,36 +1919,52 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         if ((rc = begin_timed(ctx, PH_PARTITION))) return rc;
         if ((rc = launch_scans(ctx, SP))) return rc;
         if ((rc = end_timed(ctx))) return rc;
-        // ---- K2': items of the distinct edges, level-1 prefix partition
-        ItemPartParams IP;
-        memset(&IP, 0, sizeof(IP));
-        IP.edges = ctx->edges_all_valid ? ctx->d_edges_all : ctx->d_edges;
-        IP.n_edges = ctx->edges_all_valid ? ctx->n_edges_all : ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
-        const bool segmented = ctx->edges_all_valid && !ctx->edge_segs.empty();
-        IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = nb1; IP.b1_lo = g1_lo; IP.dst = bufA; IP.cap = pl.cap;
-        IP.err = ctx->d_ctr + CTR_ERR;
+        // ---- K2': items into the batch's level-1 prefix bins at exact offsets: from the distinct edges (+ tip list), or
+        //      from the slabs the shards sent each other
         if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
-        if (segmented) {                                   // the shards' lists side by side, each padded to the longest
-            for (auto &sg : ctx->edge_segs) {
-                IP.edges = ctx->d_edges_all + sg.first * (size_t)(WE + 1);
-                IP.n_edges = sg.second;
-                if (sg.second && launch_item_part(WE, plus, false, IP, ctx->stream))
-                    FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (from_slabs) {
+            const int world = ctx->opt.world;
+            const auto &X = ctx->s2x;
+            std::vector<unsigned long long> in_start(world + 1, 0), in_count(world + 1, 0);
+            std::vector<unsigned> chunk_pref(world + 1, 0);
+            for (int sidx = 0; sidx < world; ++sidx) {
+                in_start[sidx] = (unsigned long long)sidx * IW * X.slab_items;
+                in_count[sidx] = X.counts[sidx];
+                chunk_pref[sidx + 1] = chunk_pref[sidx] + (unsigned)((X.counts[sidx] + T - 1) / T);
+            }
+            unsigned long long *d_xs = ctx->d_xs;
+            CK(cudaMemcpyAsync(d_xs, in_start.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(d_xs + (world + 1), in_count.data(), (size_t)(world + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(d_xs + 2 * (world + 1), chunk_pref.data(), (size_t)(world + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(mgta_stream_wait(ctx->stream));                       // the host vectors die with this scope
+            SplitParams X3;
+            memset(&X3, 0, sizeof(X3));
+            X3.src = reinterpret_cast<uint32_t *>(ctx->arena); X3.dst = bufA; X3.cap_src = X.slab_items; X3.cap_dst = pl.cap;
+            X3.IW = IW; X3.WE = W; X3.mode = 3; X3.sh1 = 32 - (int)lb1; X3.lb2 = lb2;
+            X3.in_start = d_xs; X3.in_count = d_xs + (world + 1); X3.chunk_pref = reinterpret_cast<unsigned *>(d_xs + 2 * (world + 1));
+            X3.B1 = (unsigned)world; X3.cursor2 = SP.cursor1; X3.ticket = ctx->d_ctr + CTR_TICKET3; X3.T = T; X3.err = ctx->d_ctr + CTR_ERR;
+            X3.b_lo = g1_lo; X3.b_hi = g1_lo + nb1; X3.slab_cap = 0; X3.bkt_lo = (unsigned)b0; X3.bkt_hi = (unsigned)b1;
+            if ((rc = launch_split(ctx, X3))) return rc;
+        } else {
+            ItemPartParams IP;
+            memset(&IP, 0, sizeof(IP));
+            IP.edges = ctx->d_edges; IP.n_edges = ctx->n_edges; IP.k = k; IP.sh1 = 32 - (int)lb1;
+            IP.bkt_lo = (unsigned)b0; IP.bkt_hi = (unsigned)b1; IP.cursor1 = SP.cursor1; IP.NB = nb1; IP.b1_lo = g1_lo; IP.dst = bufA; IP.cap = pl.cap;
+            IP.err = ctx->d_ctr + CTR_ERR;
+            if (launch_item_part(WE, plus, tips_in, IP, ctx->stream))
+                FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CK(cudaGetLastError());
+            if (tips_in && ctx->n_tips) {
+                RowPartParams RP;
+                memset(&RP, 0, sizeof(RP));
+                RP.rows = ctx->d_tips; RP.n_rows = ctx->n_tips; RP.IW = IW; RP.sh1 = IP.sh1; RP.bkt_lo = IP.bkt_lo; RP.bkt_hi = IP.bkt_hi;
+                RP.cursor1 = IP.cursor1; RP.NB = IP.NB; RP.b1_lo = IP.b1_lo; RP.dst = IP.dst; RP.cap = IP.cap; RP.err = IP.err;
+                const size_t smem = bin_smem_bytes(IW, ROW_SLOTS);
+                CK(cudaFuncSetAttribute(k_row_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_row_part<<<(unsigned)((ctx->n_tips + ROW_SLOTS - 1) / ROW_SLOTS), PART_THREADS, smem, ctx->stream>>>(RP);
+                CK(cudaGetLastError());
                 st->n_launches++;
             }
-        } else if (launch_item_part(WE, plus, tips_in, IP, ctx->stream))
-            FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        CK(cudaGetLastError());
-        if (tips_in && ctx->n_tips) {
-            RowPartParams RP;
-            memset(&RP, 0, sizeof(RP));
-            RP.rows = ctx->d_tips; RP.n_rows = ctx->n_tips; RP.IW = IW; RP.sh1 = IP.sh1; RP.bkt_lo = IP.bkt_lo; RP.bkt_hi = IP.bkt_hi;
-            RP.cursor1 = IP.cursor1; RP.NB = IP.NB; RP.b1_lo = IP.b1_lo; RP.dst = IP.dst; RP.cap = IP.cap; RP.err = IP.err;
-            const size_t smem = bin_smem_bytes(IW, ROW_SLOTS);
-            CK(cudaFuncSetAttribute(k_row_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_row_part<<<(unsigned)((ctx->n_tips + ROW_SLOTS - 1) / ROW_SLOTS), PART_THREADS, smem, ctx->stream>>>(RP);
-            CK(cudaGetLastError());
-            st->n_launches++;
         }
         if ((rc = end_timed(ctx))) return rc;
         // ---- K3a: level-2 prefix split, leaf flags, MSD levels for oversize tiles
@@ -1866,6 +2092,68 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     return MGTA_OK;
 }
 
+// ---- sharded stage 2: the items of my edges and tips, binned by the shard that emits their lv1 bucket ------------------
+// bnd[d] = first bucket of shard d (d = 0 .. world).  Arena: [recv slabs | send slabs | cursors]; the receive slabs stay
+// at the start of the arena for run_emit(from_slabs), whose buffers overlay the (then dead) send slabs.
+// expect[d]: items this shard must produce for shard d according to its own histogram (consistency check).
+int item_exchange_send(mgta_ctx *ctx, const unsigned *bnd, uint64_t slab_in, const uint64_t *expect, mgta_stage_stats *st,
+                       void **send_out, void **recv_out, uint64_t *slab_bytes) {
+    const int k = ctx->opt.kmer_k, WE = edge_words(k), W = key_words_s2(k), IW = W + 1, world = ctx->opt.world;
+    const bool plus = W > WE;
+    int rc;
+    const uint64_t slab_items = std::max<uint64_t>(32, (slab_in + 31) & ~(uint64_t)31);
+    const size_t xbytes = (size_t)world * IW * slab_items * 4, xal = (xbytes + 255) & ~(size_t)255;
+    const size_t total = 2 * xal + 4096;
+    const size_t budget = hbm_budget(ctx);
+    if (total > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold the stage-2 item exchange (%zu B)", budget, total);
+    if ((rc = ensure_arena(ctx, total))) return rc;
+    uint32_t *send = reinterpret_cast<uint32_t *>(ctx->arena + xal);
+    unsigned long long *cur = reinterpret_cast<unsigned long long *>(ctx->arena + 2 * xal);
+    const unsigned long long stride = (unsigned long long)IW * slab_items;
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, CTR_COUNT * 4, ctx->stream));
+    k_init_slab_cursors<<<1, 256, 0, ctx->stream>>>(cur, (unsigned)world, stride);
+    CK(cudaGetLastError());
+    if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
+    if (ctx->n_edges) {
+        ItemPartParams IP;
+        memset(&IP, 0, sizeof(IP));
+        IP.edges = ctx->d_edges; IP.n_edges = ctx->n_edges; IP.k = k; IP.cursor1 = cur; IP.dst = send; IP.cap = slab_items;
+        IP.err = ctx->d_ctr + CTR_ERR; IP.n_owner = world; IP.slab_cap = slab_items; IP.slab_stride = stride;
+        for (int d = 0; d <= world; ++d) IP.bnd[d] = bnd[d];
+        if (launch_item_part(WE, plus, true, IP, ctx->stream)) FAIL(MGTA_ERR_CUDA, "k_item_part launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CK(cudaGetLastError());
+        st->n_launches++;
+    }
+    if (ctx->n_tips) {
+        RowPartParams RP;
+        memset(&RP, 0, sizeof(RP));
+        RP.rows = ctx->d_tips; RP.n_rows = ctx->n_tips; RP.IW = IW; RP.cursor1 = cur; RP.dst = send; RP.cap = slab_items;
+        RP.err = ctx->d_ctr + CTR_ERR; RP.n_owner = world; RP.slab_cap = slab_items; RP.slab_stride = stride;
+        for (int d = 0; d <= world; ++d) RP.bnd[d] = bnd[d];
+        const size_t smem = bin_smem_bytes(IW, ROW_SLOTS);
+        CK(cudaFuncSetAttribute(k_row_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_row_part<<<(unsigned)((ctx->n_tips + ROW_SLOTS - 1) / ROW_SLOTS), PART_THREADS, smem, ctx->stream>>>(RP);
+        CK(cudaGetLastError());
+        st->n_launches++;
+    }
+    if ((rc = end_timed(ctx))) return rc;
+    unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
+    CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
+    if (h_ctr[CTR_ERR]) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage-2 item exchange)", h_ctr[CTR_ERR]);
+    for (int d = 0; d < world; ++d) {
+        const uint64_t got = ctx->h_pin[d] - (unsigned long long)d * stride;
+        if (got != expect[d]) FAIL(MGTA_ERR_INTERNAL, "stage-2 item exchange: %llu items for shard %d, the histogram says %llu",
+                                   (unsigned long long)got, d, (unsigned long long)expect[d]);
+    }
+    ctx->s2x.valid = false;
+    ctx->s2x.slab_items = slab_items;
+    ctx->s2x.bytes = xbytes;
+    *send_out = send; *recv_out = ctx->arena; *slab_bytes = (uint64_t)IW * slab_items * 4;
+    return MGTA_OK;
+}
+
 struct StageTimer {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -1940,7 +2228,7 @@ extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
         if ((rc = ensure_solid(ctx))) return rc;
         if ((rc = run_mercy(ctx, st))) return rc;
         ctx->edges_valid = false;
-        ctx->edges_all_valid = false;
+        ctx->s2x.valid = false;
     }
     if (edge_counting) {
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1950,23 +2238,7 @@ extern "C" int mgta_stage1(mgta_ctx *ctx, int64_t *edge_counting) {
     return stage_end(ctx, st, tm);
 }
 
-extern "C" int mgta_stage1_scan(mgta_ctx *ctx, uint64_t read_begin, uint64_t read_end, uint64_t slab_items, uint64_t *needed) {
-    if (!ctx || !needed) return MGTA_ERR_ARG;
-    if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
-    if (ctx->opt.min_count == 1) FAIL(MGTA_ERR_STATE, "stage1_scan: min_count == 1 has no stage 1");
-    if (ctx->opt.need_mercy) FAIL(MGTA_ERR_ARG, "need_mercy runs on one shard only (mgta_stage1 with world == 1)");
-    if (ctx->n_short < ctx->n_reads) FAIL(MGTA_ERR_ARG, "stage1_scan: assist reads take the replicated scan (mgta_stage1)");
-    mgta_stage_stats *st = &ctx->stats[0];
-    StageTimer tm;
-    int rc = stage_begin(ctx, st, tm);
-    if (rc) return rc;
-    ctx->solid_valid = false;
-    ctx->stage1_done = false;
-    if ((rc = exchange_scan(ctx, read_begin, read_end, slab_items, needed, st))) return rc;
-    return stage_end(ctx, st, tm);
-}
-
-extern "C" int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items) {
+static int stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items) {
     if (!ctx || !slab_items) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     const int world = ctx->opt.world;
@@ -1989,44 +2261,12 @@ extern "C" int mgta_stage1_slab_items(mgta_ctx *ctx, uint64_t *slab_items) {
     return MGTA_OK;
 }
 
-extern "C" int mgta_stage1_exchange_buffers(mgta_ctx *ctx, void **send_dev, void **recv_dev, uint64_t *slab_bytes,
-                                            uint64_t *send_counts) {
-    if (!ctx || !send_dev || !recv_dev || !slab_bytes || !send_counts) return MGTA_ERR_ARG;
-    if (!ctx->xch.valid) FAIL(MGTA_ERR_STATE, "no exchange pending: call mgta_stage1_scan first");
-    *send_dev = ctx->arena + ctx->xch.send_off;
-    *recv_dev = ctx->arena + ctx->xch.recv_off;
-    *slab_bytes = (uint64_t)ctx->xch.cp.IW * ctx->xch.slab_items * 4;
-    for (int d = 0; d < ctx->opt.world; ++d) send_counts[d] = ctx->xch.send_counts[d];
-    return MGTA_OK;
-}
-
-extern "C" int mgta_stage1_count(mgta_ctx *ctx, const uint64_t *recv_counts, int64_t *edge_counting) {
-    if (!ctx || !recv_counts) return MGTA_ERR_ARG;
-    mgta_stage_stats scan = ctx->stats[0], *st = &ctx->stats[0];
-    StageTimer tm;
-    int rc = stage_begin(ctx, st, tm);
-    if (rc) return rc;
-    st->key_words = scan.key_words; st->item_words = scan.item_words; st->sort_cap = scan.sort_cap;
-    if ((rc = exchange_count(ctx, recv_counts, st))) return rc;
-    ctx->stage1_done = true;
-    st->n_edges = ctx->n_edges;
-    if (edge_counting) {
-        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_ec, NUM_BUCKETS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(mgta_stream_wait(ctx->stream));
-        for (int i = 0; i < NUM_BUCKETS; ++i) edge_counting[i] = (int64_t)ctx->h_pin[i];
-    }
-    if ((rc = stage_end(ctx, st, tm))) return rc;
-    st->ms_total += scan.ms_total; st->ms_extract += scan.ms_extract; st->n_launches += scan.n_launches;
-    st->n_giants += scan.n_giants;
-    return MGTA_OK;
-}
-
 extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals) {
     if (!ctx) return MGTA_ERR_ARG;
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     // several shards: this shard's edge list alone would give a self-consistent but partial graph
-    if (ctx->opt.world > 1 && ctx->edges_valid && !ctx->edges_all_valid && !ctx->edges_complete)
-        FAIL(MGTA_ERR_STATE, "stage 2 on %d shards needs the solid edges of all shards: exchange them (mgta_edges_reserve) first", ctx->opt.world);
+    if (ctx->opt.world > 1 && ctx->edges_valid && !ctx->edges_complete)
+        FAIL(MGTA_ERR_STATE, "this shard holds the solid edges of its hash range only: stage 2 on %d shards runs through mgta_sharded_begin / _step", ctx->opt.world);
     mgta_stage_stats *st = &ctx->stats[1];
     StageTimer tm;
     int rc = stage_begin(ctx, st, tm);
@@ -2039,7 +2279,7 @@ extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int
         if ((rc = run_count(ctx, CM_GENERAL, &tmp))) return rc;
         st->n_launches += tmp.n_launches;
     }
-    if (ctx->node_pass && !ctx->edges_all_valid && !ctx->tips_valid && (rc = run_nodes(ctx, st))) return rc;
+    if (ctx->node_pass && !ctx->tips_valid && (rc = run_nodes(ctx, st))) return rc;
     if ((rc = run_emit(ctx, sink, user, totals, st))) return rc;
     if (ctx->node_pass && ctx->tips_valid) { st->n_node_ops = 2 * ctx->n_edges; st->n_tip_items = ctx->n_tips; }
     return stage_end(ctx, st, tm);
@@ -2102,7 +2342,7 @@ extern "C" int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_
     CK(mgta_stream_wait(ctx->stream));
     cudaFree(tmp);
     ctx->edges_valid = false;
-    ctx->edges_all_valid = false;
+    ctx->s2x.valid = false;
     ctx->solid_valid = true;
     return MGTA_OK;
 }
@@ -2125,44 +2365,6 @@ extern "C" int mgta_get_num_mercy(mgta_ctx *ctx, uint64_t *num_mercy) {
     if (!ctx || !num_mercy) return MGTA_ERR_ARG;
     if (!ctx->mercy_valid) FAIL(MGTA_ERR_STATE, "no mercy result: run mgta_stage1 with need_mercy first");
     *num_mercy = ctx->num_mercy;
-    return MGTA_OK;
-}
-
-extern "C" int mgta_edges_local(mgta_ctx *ctx, void **dev, uint64_t *n_rows, int32_t *row_words) {
-    if (!ctx || !dev || !n_rows || !row_words) return MGTA_ERR_ARG;
-    if (!ctx->edges_valid) FAIL(MGTA_ERR_STATE, "no edge list: run mgta_stage1 first");
-    *dev = ctx->d_edges; *n_rows = ctx->n_edges; *row_words = ctx->edge_row_words;
-    return MGTA_OK;
-}
-
-extern "C" int mgta_edges_reserve(mgta_ctx *ctx, uint64_t n_rows_total, uint64_t my_offset_rows, void **dev) {
-    if (!ctx || !dev) return MGTA_ERR_ARG;
-    if (!ctx->edges_valid) FAIL(MGTA_ERR_STATE, "no edge list: run mgta_stage1 first");
-    if (my_offset_rows + ctx->n_edges > n_rows_total) FAIL(MGTA_ERR_ARG, "edges_reserve: local rows do not fit at that offset");
-    CK(cudaSetDevice(ctx->opt.device));
-    const size_t row = (size_t)ctx->edge_row_words * 4;
-    if (n_rows_total > ctx->edges_all_cap || !ctx->d_edges_all) {  // grows only: no allocation on the steady-state path
-        CK(mgta_stream_wait(ctx->stream));
-        cudaFree(ctx->d_edges_all);
-        ctx->d_edges_all = nullptr; ctx->edges_all_cap = 0;
-        const uint64_t ncap = n_rows_total + n_rows_total / 16 + 64;
-        CK(cudaMalloc(&ctx->d_edges_all, ncap * row));
-        ctx->edges_all_cap = ncap;
-    }
-    if (ctx->n_edges)
-        CK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ctx->d_edges_all) + my_offset_rows * row, ctx->d_edges, ctx->n_edges * row,
-                           cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(mgta_stream_wait(ctx->stream));
-    ctx->n_edges_all = n_rows_total;
-    ctx->edges_all_valid = true;
-    ctx->edge_segs.clear();
-    *dev = ctx->d_edges_all;
-    return MGTA_OK;
-}
-
-extern "C" int mgta_edge_hist_device_buffer(mgta_ctx *ctx, void **dev, uint64_t *n_bytes) {
-    if (!ctx || !dev || !n_bytes) return MGTA_ERR_ARG;
-    *dev = ctx->d_hist_s2; *n_bytes = ((uint64_t)1 << ctx->PB) * 4;
     return MGTA_OK;
 }
 

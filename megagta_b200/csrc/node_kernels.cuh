@@ -32,6 +32,11 @@ struct NodePartParams {
     uint32_t *dst;
     uint64_t cap;
     unsigned *err;
+    // sharded (n_owner > 0): the bin of an op is the SHARD that owns its level-1 hash bin (owner d holds bins
+    // [owner_lo[d], owner_lo[d + 1])); slab d starts at item index d * slab_stride, holds slab_cap ops; no tile histogram
+    int n_owner;
+    unsigned owner_lo[MAX_OWNERS + 1];
+    unsigned long long slab_stride;
 };
 
 constexpr int NODE_EDGES = 1024;      // edges per CTA -> 2048 op slots
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_node_part(const NodePartParams
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, SLOTS);
     const int tid = threadIdx.x;
-    const int NB = (int)(P.b_hi - P.b_lo);
+    const int NB = P.n_owner ? P.n_owner : (int)(P.b_hi - P.b_lo);
     for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
     for (int i = tid; i < SLOTS; i += PART_THREADS) S.bin[i] = 0xFFFFu;
     __syncthreads();
@@ -64,10 +69,17 @@ __global__ void __launch_bounds__(PART_THREADS) k_node_part(const NodePartParams
             uint32_t ha, hb;
             edge_hash([&](int w) { return c[w]; }, KW, ha, hb);
             const unsigned b1 = ha >> P.sh1;
-            if (b1 >= P.b_lo && b1 < P.b_hi) {
+            if (P.n_owner || (b1 >= P.b_lo && b1 < P.b_hi)) {
                 const int slot = el * 2 + j;
-                const unsigned bin = b1 - P.b_lo;
-                atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & sub_mask)), 1u);
+                unsigned bin;
+                if (P.n_owner) {
+                    bin = 0;
+#pragma unroll
+                    for (int i = 1; i < MAX_OWNERS; ++i) bin += (i < P.n_owner && b1 >= P.owner_lo[i]) ? 1u : 0u;
+                } else {
+                    bin = b1 - P.b_lo;
+                    atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & sub_mask)), 1u);
+                }
 #pragma unroll
                 for (int w = 0; w < KW; ++w) S.stage[w * SLOTS + slot] = c[w];
                 S.stage[KW * SLOTS + slot] = (wgt << 1) | (uint32_t)dir;
@@ -78,7 +90,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_node_part(const NodePartParams
         });
     }
     __syncthreads();
-    bin_scatter(S, SLOTS, IW, SLOTS, NB, P.cursor1, P.dst, P.cap, P.slab_cap, P.err);
+    bin_scatter(S, SLOTS, IW, SLOTS, NB, P.cursor1, P.dst, P.cap, P.slab_cap, P.err, P.n_owner ? P.slab_stride : 0ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,6 +300,11 @@ struct RowPartParams {
     uint32_t *dst;
     uint64_t cap;
     unsigned *err;
+    // sharded (n_owner > 0): bin = the shard whose lv1-bucket range [bnd[d], bnd[d + 1]) holds the item; slab d starts at
+    // item index d * slab_stride and holds slab_cap items
+    int n_owner;
+    unsigned bnd[MAX_OWNERS + 1];
+    unsigned long long slab_cap, slab_stride;
 };
 
 constexpr int ROW_SLOTS = 2048;
@@ -298,7 +315,8 @@ __global__ void __launch_bounds__(PART_THREADS) k_row_part(const RowPartParams P
     const int IW = P.IW;
     bin_smem_carve(S, smem_raw, IW, ROW_SLOTS);
     const int tid = threadIdx.x;
-    for (int i = tid; i < (int)P.NB; i += PART_THREADS) S.cnt[i] = 0;
+    const int NB = P.n_owner ? P.n_owner : (int)P.NB;
+    for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
     __syncthreads();
     const unsigned long long r0 = (unsigned long long)blockIdx.x * ROW_SLOTS;
     for (int sl = tid; sl < ROW_SLOTS; sl += PART_THREADS) {
@@ -308,8 +326,14 @@ __global__ void __launch_bounds__(PART_THREADS) k_row_part(const RowPartParams P
             const uint32_t *row = P.rows + r * IW;
             const uint32_t y0 = __ldg(row);
             const unsigned bkt = y0 >> 16;
-            if (bkt >= P.bkt_lo && bkt < P.bkt_hi) {
-                bin = (y0 >> P.sh1) - P.b1_lo;
+            if (P.n_owner || (bkt >= P.bkt_lo && bkt < P.bkt_hi)) {
+                if (P.n_owner) {
+                    bin = 0;
+#pragma unroll
+                    for (int i = 1; i < MAX_OWNERS; ++i) bin += (i < P.n_owner && bkt >= P.bnd[i]) ? 1u : 0u;
+                } else {
+                    bin = (y0 >> P.sh1) - P.b1_lo;
+                }
                 for (int w = 0; w < IW; ++w) S.stage[w * ROW_SLOTS + sl] = __ldg(row + w);
                 S.rank[sl] = (uint16_t)atomicAdd(&S.cnt[bin], 1u);
             }
@@ -317,7 +341,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_row_part(const RowPartParams P
         S.bin[sl] = (uint16_t)bin;
     }
     __syncthreads();
-    bin_scatter(S, ROW_SLOTS, IW, ROW_SLOTS, (int)P.NB, P.cursor1, P.dst, P.cap, 0ull, P.err);
+    bin_scatter(S, ROW_SLOTS, IW, ROW_SLOTS, NB, P.cursor1, P.dst, P.cap, P.n_owner ? P.slab_cap : 0ull, P.err, P.n_owner ? P.slab_stride : 0ull);
 }
 
 }  // namespace mgta

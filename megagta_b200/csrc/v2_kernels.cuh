@@ -156,6 +156,9 @@ struct EdgePartParams {
     uint64_t g_begin, g_end;        // base range of this launch (g_begin a multiple of 1024); all modes
     uint64_t r_begin;
     unsigned long long slab_stride;
+    // rounds (n_rounds > 1, HBM too small for all items at once): this scan keeps only the items whose level-1 bin lies in
+    // slice `round` of its owner's bins, [lo + cnt * round / n_rounds, lo + cnt * (round + 1) / n_rounds)
+    unsigned n_rounds, round;
 };
 
 // PW = payload words: 0 none, 1 = base position (u32), 2 = base position (lo, hi)
@@ -237,8 +240,12 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
                     unsigned d = 0;
 #pragma unroll
                     for (int i = 1; i < MAX_OWNERS; ++i) d += (i < P.n_owner && b1 >= P.owner_lo[i]) ? 1u : 0u;
-                    bin = d;
                     mine = true;
+                    if (P.n_rounds > 1) {
+                        const unsigned lo = P.owner_lo[d], cnt = P.owner_lo[d + 1] - lo, off = b1 - lo;
+                        mine = off >= cnt * P.round / P.n_rounds && off < cnt * (P.round + 1) / P.n_rounds;
+                    }
+                    if (mine) bin = d;
                 } else {
                     mine = b1 >= P.b_lo && b1 < P.b_hi;
                     if (mine) {
@@ -359,6 +366,7 @@ struct SplitParams {
     int IW, WE;
     int mode;                            // 0: hash of the WE key words, 1: prefix bits of key word 0,
                                          // 2: level-1 hash bin of items received from the other shards (see below)
+                                         // 3: level-1 PREFIX bin of stage-2 items received from the other shards
     int sh2;                             // tile = x >> sh2 (x = ha or key word 0)
     unsigned lb2;
     const unsigned long long *in_start;  // [B1]
@@ -377,6 +385,9 @@ struct SplitParams {
     unsigned long long slab_cap;
     uint32_t *hist2;
     uint32_t drop_last;                  // bits of the last hashed key word that do not take part in the hash (mercy items: head/tail flags)
+    // mode 3: like mode 2 with bin = key word 0 >> sh1 (global level-1 prefix bin; [b_lo, b_hi) = the batch's bins), only
+    // items of lv1 buckets [bkt_lo, bkt_hi), exact cursors (cursor2[bin], slab_cap = 0), no histogram
+    unsigned bkt_lo, bkt_hi;
 };
 
 __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
     BinSmem S;
     const int T = (int)P.T, IW = P.IW, tid = threadIdx.x;
     bin_smem_carve(S, smem_raw, IW, T);
-    const int NB = P.mode == 2 ? (int)(P.b_hi - P.b_lo) : 1 << P.lb2;
+    const int NB = P.mode >= 2 ? (int)(P.b_hi - P.b_lo) : 1 << P.lb2;
     const unsigned n_jobs = P.chunk_pref[P.B1];
     if (*P.err & ERR_SLAB_OVERFLOW) return;
     while (true) {
@@ -417,17 +428,18 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
         __syncthreads();
         for (int i = tid; i < n; i += PART_THREADS) {
             uint32_t x;
-            if (P.mode != 1) {
+            if (P.mode == 0 || P.mode == 2) {
                 uint32_t hb;
                 edge_hash([&](int w) { const uint32_t v = S.stage[w * T + i]; return w == P.WE - 1 ? v & ~P.drop_last : v; }, P.WE, x, hb);
             } else {
                 x = S.stage[i];
             }
-            if (P.mode == 2) {
+            if (P.mode >= 2) {
                 const unsigned bb = x >> P.sh1;
-                if (bb >= P.b_lo && bb < P.b_hi) {
+                const bool in_bkt = P.mode == 2 || ((x >> 16) >= P.bkt_lo && (x >> 16) < P.bkt_hi);
+                if (bb >= P.b_lo && bb < P.b_hi && in_bkt) {
                     const unsigned b = bb - P.b_lo;
-                    atomicAdd(P.hist2 + ((b << P.lb2) | ((x >> P.sh2) & ((1u << P.lb2) - 1u))), 1u);
+                    if (P.mode == 2) atomicAdd(P.hist2 + ((b << P.lb2) | ((x >> P.sh2) & ((1u << P.lb2) - 1u))), 1u);
                     S.bin[i] = (uint16_t)b;
                     S.rank[i] = (uint16_t)atomicAdd(&S.cnt[b], 1u);
                 } else {
@@ -440,7 +452,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
             S.rank[i] = (uint16_t)atomicAdd(&S.cnt[b2], 1u);
         }
         __syncthreads();
-        if (P.mode == 2) bin_scatter(S, n, IW, T, NB, P.cursor2, P.dst, P.cap_dst, P.slab_cap, P.err);
+        if (P.mode >= 2) bin_scatter(S, n, IW, T, NB, P.cursor2, P.dst, P.cap_dst, P.slab_cap, P.err);
         else bin_scatter(S, n, IW, T, NB, P.cursor2 + ((size_t)b1 << P.lb2), P.dst, P.cap_dst, 0ull, P.err);
     }
 }
@@ -715,6 +727,11 @@ struct ItemPartParams {
     uint32_t *dst;
     uint64_t cap;
     unsigned *err;
+    // sharded (n_owner > 0): bin = the shard whose lv1-bucket range [bnd[d], bnd[d + 1]) holds the item (no bucket filter);
+    // slab d starts at item index d * slab_stride and holds slab_cap items
+    int n_owner;
+    unsigned bnd[MAX_OWNERS + 1];
+    unsigned long long slab_cap, slab_stride;
 };
 
 constexpr int ITEM_SLOTS = 3072;      // item slots per CTA: 512 edges x 6 items, or 1536 edges x 2 real items
@@ -729,7 +746,8 @@ __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, SLOTS);
     const int tid = threadIdx.x;
-    for (int i = tid; i < (int)P.NB; i += PART_THREADS) S.cnt[i] = 0;
+    const int NB = P.n_owner ? P.n_owner : (int)P.NB;
+    for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
     for (int i = tid; i < SLOTS; i += PART_THREADS) S.bin[i] = 0xFFFFu;
     __syncthreads();
     const unsigned long long e0 = (unsigned long long)blockIdx.x * EDGES;
@@ -744,9 +762,16 @@ __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams
         int j = 0;
         s2_items_of_edge<W2, WE>(key, P.k, [&](const uint32_t(&y)[W2]) {
             const unsigned bkt = y[0] >> 16;
-            if (bkt >= P.bkt_lo && bkt < P.bkt_hi) {
+            if (P.n_owner || (bkt >= P.bkt_lo && bkt < P.bkt_hi)) {
                 const int slot = el * PER + j;
-                const unsigned b = (y[0] >> P.sh1) - P.b1_lo;
+                unsigned b;
+                if (P.n_owner) {
+                    b = 0;
+#pragma unroll
+                    for (int i = 1; i < MAX_OWNERS; ++i) b += (i < P.n_owner && bkt >= P.bnd[i]) ? 1u : 0u;
+                } else {
+                    b = (y[0] >> P.sh1) - P.b1_lo;
+                }
 #pragma unroll
                 for (int w = 0; w < W2; ++w) S.stage[w * SLOTS + slot] = y[w];
                 S.stage[W2 * SLOTS + slot] = mult;
@@ -757,7 +782,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams
         }, PER == 6);
     }
     __syncthreads();
-    bin_scatter(S, SLOTS, IW, SLOTS, (int)P.NB, P.cursor1, P.dst, P.cap, 0ull, P.err);
+    bin_scatter(S, SLOTS, IW, SLOTS, NB, P.cursor1, P.dst, P.cap, P.n_owner ? P.slab_cap : 0ull, P.err, P.n_owner ? P.slab_stride : 0ull);
 }
 
 // leaf-start flags of the non-empty tiles of a batch (the on-chip sort's windows never straddle a leaf)

@@ -58,8 +58,8 @@ def main():
             else:
                 ctx.alloc_reads(n_words, n_reads, n_reads, total_bases, max_len)
             (sp, sb), (tp, tb) = ctx.reads_device_buffers()
-            dist.broadcast(torch.as_tensor(shards.DevBuf(sp, sb), device=dev), 0)
-            dist.broadcast(torch.as_tensor(shards.DevBuf(tp, tb), device=dev), 0)
+            dist.broadcast(torch.as_tensor(shards.ByteBuf(sp, sb), device=dev), 0)
+            dist.broadcast(torch.as_tensor(shards.ByteBuf(tp, tb), device=dev), 0)
             # the library walks the protocol; TorchComm runs the collectives it asks for with NCCL
             ec_np, (st, meta, totals) = shards.build_sharded(ctx, rank, world, dist, dev)
             ec = torch.from_numpy(ec_np if ec_np is not None else np.zeros(65536, dtype=np.int64)).to(dev)

@@ -1,5 +1,5 @@
 """Real multi-GPU parity (one process per GPU, NCCL): skipped on boxes with a single GPU.  The single-device tests
-test_gpu_shards_concatenate_to_the_whole_graph / test_gpu_edge_exchange_between_shards cover the same flow there."""
+tests/test_gpu_sharded.py walks the same protocol with all shards on one device."""
 import os
 import socket
 import subprocess

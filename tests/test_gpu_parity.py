@@ -137,144 +137,6 @@ def test_gpu_shards_concatenate_to_the_whole_graph(read_lib):
                 c.close()
 
 
-def _dev_tensor(ptr, nbytes):
-    import torch
-
-    class _Buf:
-        __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr, False), "version": 3}
-    return torch.as_tensor(_Buf(), device="cuda:0")
-
-
-@pytest.mark.parametrize("ds,k,m", [("smoke", 31, 2), ("adversarial", 27, 3), ("meta200k", 61, 2)])
-def test_gpu_edge_exchange_between_shards(read_lib, ds, k, m):
-    """The hot multi-GPU flow on one device: hash-sharded stage 1, all-gather of the solid-edge rows, all-reduce of
-    the stage-2 prefix histogram, bucket-sharded stage 2 (what bench.py does with NCCL)."""
-    import torch
-    _, rd = read_lib(ds)
-    whole = run_gpu(rd, k, m)
-    for world in (2, 5):
-        ctxs = [cabi.Context(k, m, rank=r, world=world) for r in range(world)]
-        try:
-            ec = np.zeros(65536, dtype=np.int64)
-            for c in ctxs:
-                c.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
-                ec += c.stage1()
-            assert np.array_equal(ec, whole["counting"])
-            rows = [c.edges_local() for c in ctxs]
-            n = [r[1] for r in rows]
-            w = rows[0][2]
-            offs = np.concatenate([[0], np.cumsum(n)]).astype(int)
-            total = int(offs[-1])
-            parts = [_dev_tensor(r[0], r[1] * w * 4).clone() if r[1] else None for r in rows]
-            hists = []
-            for c in ctxs:
-                p, nb = c.edge_hist_device_buffer()
-                hists.append(_dev_tensor(p, nb))
-            hsum = torch.stack(hists).sum(dim=0, dtype=torch.int32)
-            for r, c in enumerate(ctxs):
-                p = c.edges_reserve(total, int(offs[r]))
-                buf = _dev_tensor(p, max(total, 1) * w * 4)
-                for j in range(world):
-                    if j != r and n[j]:
-                        buf[offs[j] * w:(offs[j] + n[j]) * w] = parts[j]
-                hists[r].copy_(hsum)
-            torch.cuda.synchronize()
-            streams, meta = [], np.zeros((65536, 3), dtype=np.int64)
-            totals = np.zeros(10, dtype=np.int64)
-            for c in ctxs:
-                st, mt, tt = c.stage2()
-                streams.append(st)
-                meta += mt
-                totals += tt
-            assert b"".join(streams) == whole["stream"]
-            assert np.array_equal(meta, whole["meta"])
-            assert np.array_equal(totals, whole["totals"])
-        finally:
-            for c in ctxs:
-                c.close()
-
-
-@pytest.mark.parametrize("ds,k,m,cap", [("smoke", 31, 2, 0), ("meta200k", 61, 2, 0), ("adversarial", 27, 3, 0), ("tiny", 25, 2, 64),
-                                         ("xander", 44, 2, 0)])
-def test_gpu_scan_sharded_stage1_exchange(read_lib, ds, k, m, cap):
-    """The scan-sharded stage 1 on one device: every shard extracts the items of ITS slice of the reads binned by owner
-    shard, the all-to-all (here: device copies between the contexts) moves them, every shard counts what it received.
-    edge_counting, the solid-edge rows and, after the edge exchange, the SdBG stream must equal the single-shard run."""
-    import torch
-    from megagta_b200 import shards
-    _, rd = read_lib(ds)
-    whole = run_gpu(rd, k, m)
-    n_reads = len(rd["start"]) - 1
-    for world in (2, 3):
-        ctxs = [cabi.Context(k, m, rank=r, world=world, sort_items_cap=cap) for r in range(world)]
-        try:
-            bufs = []
-            for c in ctxs:
-                c.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
-            ranges = [shards.read_range(n_reads, r, world) for r in range(world)]
-            sizes = {c.stage1_slab_items() for c in ctxs}
-            assert len(sizes) == 1                       # every shard derives the same slab size from start_idx: no agreement round
-            assert max(c.stage1_scan(lo, hi, 0) for c, (lo, hi) in zip(ctxs, ranges)) <= min(sizes)
-            slab = 64 if cap else min(sizes)
-            need = max(c.stage1_scan(lo, hi, slab) for c, (lo, hi) in zip(ctxs, ranges))
-            if cap:
-                assert need > slab                       # the 64-item slabs must overflow and report the size that fits
-            if need > slab:
-                slab = need
-                assert max(c.stage1_scan(lo, hi, slab) for c, (lo, hi) in zip(ctxs, ranges)) == slab
-            for c in ctxs:
-                sp, rp, sb, cnt = c.stage1_exchange_buffers()
-                bufs.append((_dev_tensor(sp, world * sb), _dev_tensor(rp, world * sb), sb // 4, cnt))
-            assert len({b[2] for b in bufs}) == 1
-            ws = bufs[0][2]
-            for d in range(world):                       # all-to-all: slab d of shard s -> slab s of shard d
-                for s_ in range(world):
-                    bufs[d][1][s_ * ws:(s_ + 1) * ws] = bufs[s_][0][d * ws:(d + 1) * ws]
-            torch.cuda.synchronize()
-            ec = np.zeros(65536, dtype=np.int64)
-            for d, c in enumerate(ctxs):
-                ec += c.stage1_count([int(bufs[s_][3][d]) for s_ in range(world)])
-            assert np.array_equal(ec, whole["counting"])
-            # edge exchange + stage 2 as in test_gpu_edge_exchange_between_shards
-            rows = [c.edges_local() for c in ctxs]
-            n = [r[1] for r in rows]
-            w = rows[0][2]
-            offs = np.concatenate([[0], np.cumsum(n)]).astype(int)
-            total = int(offs[-1])
-            parts = [_dev_tensor(r[0], r[1] * w * 4).clone() if r[1] else None for r in rows]
-            hists = []
-            for c in ctxs:
-                p, nb = c.edge_hist_device_buffer()
-                hists.append(_dev_tensor(p, nb))
-            hsum = torch.stack(hists).sum(dim=0, dtype=torch.int32)
-            for r, c in enumerate(ctxs):
-                p = c.edges_reserve(total, int(offs[r]))
-                buf = _dev_tensor(p, max(total, 1) * w * 4)
-                for j in range(world):
-                    if j != r and n[j]:
-                        buf[offs[j] * w:(offs[j] + n[j]) * w] = parts[j]
-                hists[r].copy_(hsum)
-            torch.cuda.synchronize()
-            streams, meta = [], np.zeros((65536, 3), dtype=np.int64)
-            totals = np.zeros(10, dtype=np.int64)
-            for c in ctxs:
-                st, mt, tt = c.stage2()
-                streams.append(st)
-                meta += mt
-                totals += tt
-            assert b"".join(streams) == whole["stream"]
-            assert np.array_equal(meta, whole["meta"])
-            assert np.array_equal(totals, whole["totals"])
-            nb = (max(0, rd["max_len"] - k) * n_reads + 7) // 8
-            got = np.zeros(nb + 8, dtype=np.uint8)
-            for c in ctxs:                               # is_solid: every shard derives the bits of its hash range
-                got |= c.get_is_solid()
-            assert np.array_equal(got[:nb], whole["is_solid"][:nb])
-        finally:
-            for c in ctxs:
-                c.close()
-
-
 @pytest.mark.parametrize("ds,k,m", [("smoke", 31, 2), ("smoke", 31, 1), ("adversarial", 27, 3), ("meta200k", 61, 2), ("tiny", 25, 2)])
 def test_gpu_assist_reads_match_oracle(read_lib, data_dir, ds, k, m):
     """Assist reads (mgta_set_reads n_short_reads < n_reads; reference s1.cpp:104-134, s2.cpp:276,529): they count in

@@ -114,6 +114,28 @@ def test_sharded_protocol_with_small_tables_and_budget(read_lib):
     check_world(rd, 31, 2, 4, whole, hbm_budget_bytes=200 << 20)
 
 
+def test_sharded_protocol_with_overflowing_send_slabs(read_lib, monkeypatch):
+    """send slabs of 64 items (MGTA_TEST_SLAB_ITEMS, the test hook of the stage-1 and node-pass scans) overflow on every
+    shard: the all-gathered table reports the size that fits and every shard rescans once"""
+    _, rd = read_lib("smoke")
+    whole = one_shard(rd, 31, 2)
+    monkeypatch.setenv("MGTA_TEST_SLAB_ITEMS", "64")
+    s1, s2 = check_world(rd, 31, 2, 3, whole)
+    assert s1["n_giants"] >= 1                                  # stage 1 counted its rescan
+
+
+def test_sharded_stage1_in_rounds(read_lib, monkeypatch):
+    """inputs whose stage-1 items do not fit the HBM at once are exchanged in rounds (one slice of every shard's hash range
+    per round, the reads scanned again each time); MGTA_TEST_ROUNDS forces three rounds on a small input"""
+    _, rd = read_lib("meta200k")
+    whole = one_shard(rd, 31, 2)
+    monkeypatch.setenv("MGTA_TEST_ROUNDS", "3")
+    s1, _ = check_world(rd, 31, 2, 2, whole)
+    assert s1["n_batches"] >= 3
+    monkeypatch.setenv("MGTA_TEST_ROUNDS", "5")
+    check_world(rd, 61, 2, 3, one_shard(rd, 61, 2))
+
+
 def test_sharded_protocol_with_assist_reads(read_lib, data_dir):
     import datasets
     _, rd = read_lib("smoke")

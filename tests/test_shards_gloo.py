@@ -1,5 +1,5 @@
-"""world_size-2 (and 3) gloo test of the multi-GPU exchange plumbing (megagta_b200/shards.py) with fake shards on the
-CPU: every rank must end up with all rows in rank order and the summed histogram."""
+"""world_size-2 (and 3) gloo tests of the multi-GPU plumbing (megagta_b200/shards.py) on the CPU: the four collectives the
+library's sharded protocol asks its caller to run (include/mgta_cuda.h mgta_collective), on byte tensors."""
 import os
 import socket
 
@@ -16,124 +16,6 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
-
-
-def _rows(rank, row_words):
-    rng = np.random.default_rng(100 + rank)
-    n = [7, 0, 12, 3][rank % 4] if rank != 1 else 5
-    return torch.from_numpy(rng.integers(-2**31, 2**31 - 1, size=(n, row_words), dtype=np.int64).astype(np.int32))
-
-
-def _worker(rank, world, port, row_words, out):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        local = _rows(rank, row_words)
-        hist = torch.full((64,), rank + 1, dtype=torch.int32)
-        holder = {}
-
-        def reserve(total, off):
-            buf = torch.zeros(max(total, 1) * row_words, dtype=torch.int32)
-            buf[off * row_words:(off + len(local)) * row_words] = local.reshape(-1)
-            holder["buf"] = buf
-            return buf
-
-        counts, offs = shards.exchange(rank, world, dist, torch.device("cpu"), len(local), row_words, reserve, hist)
-        exp = torch.cat([_rows(r, row_words) for r in range(world)]).reshape(-1)
-        ok = counts == [len(_rows(r, row_words)) for r in range(world)] and offs[-1] * row_words == len(exp) \
-            and torch.equal(holder["buf"][:len(exp)], exp) and bool((hist == world * (world + 1) // 2).all())
-        out[rank] = bool(ok)
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("world", [2, 3])
-def test_edge_exchange_over_gloo(world):
-    mgr = mp.Manager()
-    out = mgr.dict()
-    port = _free_port()
-    mp.spawn(_worker, args=(world, port, 3, out), nprocs=world, join=True)
-    assert dict(out) == {r: True for r in range(world)}
-
-
-def test_plan_offsets():
-    assert shards.plan([3, 0, 5]) == [0, 3, 3, 8]
-
-
-class _FakeCtx:
-    """Stands in for cabi.Context in the scan-sharded stage-1 driver: 'items' are int32 words tagged with (source, dest),
-    the first scan overflows when `skew` is set (so the agreed rescan path is exercised)."""
-
-    def __init__(self, rank, world, skew):
-        self.rank, self.world, self.skew = rank, world, skew
-        self.slab_words = 0
-        self.scans = 0
-
-    def counts(self):
-        return [3 + 2 * self.rank + d + (40 if self.skew and self.rank == 1 and d == 0 else 0) for d in range(self.world)]
-
-    def stage1_slab_items(self):
-        return 16
-
-    def stage1_scan(self, lo, hi, slab):
-        self.scans += 1
-        need = max(max(self.counts()), slab)
-        if need > slab:
-            return need
-        self.slab_words = slab
-        self.send = torch.zeros(self.world * slab, dtype=torch.int32)
-        for d, c in enumerate(self.counts()):
-            self.send[d * slab:d * slab + c] = 1000 * self.rank + 10 * d + 1
-        self.recv = torch.full((self.world * slab,), -1, dtype=torch.int32)
-        return slab
-
-    def stage1_exchange_buffers(self):
-        return self.send, self.recv, self.slab_words * 4, self.counts()
-
-    def stage1_count(self, got):
-        self.got = got
-        return np.zeros(4, dtype=np.int64)
-
-
-def _worker_items(rank, world, port, skew, out):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        ctx = _FakeCtx(rank, world, skew)
-        orig = shards.DevBuf
-        shards.DevBuf = lambda t, nbytes: t            # the fake buffers are tensors already
-        as_tensor = torch.as_tensor
-        try:
-            torch.as_tensor = lambda x, device=None, **kw: x if isinstance(x, torch.Tensor) else as_tensor(x, **kw)
-            shards.stage1_scan_sharded(ctx, 1000, rank, world, dist, torch.device("cpu"))
-        finally:
-            torch.as_tensor = as_tensor
-            shards.DevBuf = orig
-        slab = ctx.slab_words
-        ok = ctx.scans == (2 if skew else 1)
-        for s in range(world):
-            c = _FakeCtx(s, world, skew).counts()[rank]
-            ok = ok and ctx.got[s] == c and bool((ctx.recv[s * slab:s * slab + c] == 1000 * s + 10 * rank + 1).all())
-        out[rank] = bool(ok)
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("world,skew", [(2, False), (3, False), (2, True)])
-def test_stage1_item_exchange_over_gloo(world, skew):
-    """scan -> one all-gather of (counts, need) -> agreed rescan on overflow -> equal-split all-to-all -> count"""
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_worker_items, args=(world, _free_port(), skew, out), nprocs=world, join=True)
-    assert dict(out) == {r: True for r in range(world)}
-
-
-def test_read_ranges_partition_the_reads():
-    for n, w in [(10, 3), (1000, 7), (5, 8)]:
-        r = [shards.read_range(n, i, w) for i in range(w)]
-        assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
 
 
 # ---- the library-driven protocol: the four collectives of include/mgta_cuda.h on byte tensors ---------------------------
