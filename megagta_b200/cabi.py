@@ -207,7 +207,8 @@ class Context:
 
         def sink(user, b0, b1, ptr, nbytes, mptr):
             if nbytes and collect is True:
-                parts.append(ctypes.string_at(ptr, nbytes))
+                for o in range(0, nbytes, 1 << 30):          # ctypes.string_at takes a C int size: slices of 1 GiB
+                    parts.append(ctypes.string_at(ptr + o, min(1 << 30, nbytes - o)))
             nbytes_total[0] += nbytes
             meta[b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
             return 0
@@ -225,7 +226,8 @@ class Context:
 
         def sink(user, b0, b1, ptr, nbytes, mptr):
             if nbytes and collect is True:
-                sh["parts"].append(ctypes.string_at(ptr, nbytes))
+                for o in range(0, nbytes, 1 << 30):          # ctypes.string_at takes a C int size: slices of 1 GiB
+                    sh["parts"].append(ctypes.string_at(ptr + o, min(1 << 30, nbytes - o)))
             sh["nbytes"] += nbytes
             sh["meta"][b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
             return 0

@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
     if (tid < 10) s_tot10[tid] = 0;
 
     for (unsigned iter = 0;; ++iter) {
-        if (tid == 0) s_j2[iter & 1] = atomicAdd(P.ticket, 1u);
+        if (tid == 0) s_j2[iter & 1] = P.win_lo + atomicAdd(P.ticket, 1u);
         __syncthreads();
         const unsigned j = s_j2[iter & 1];
-        if (j >= P.n_windows) break;
+        if (j >= P.win_hi) break;
         if (warp == 0) { unsigned long long v = window_lo(P, j); if (lane == 0) s_lo = v; }
         if (warp == 1) { unsigned long long v = window_lo(P, j + 1); if (lane == 0) s_hi = v; }
         __syncthreads();
@@ -437,15 +437,16 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
 
 // ---- window order: exclusive scan of the window byte counts, then a copy of every window to its final place
 // state layout: [0] cursor, then per window (temp offset, bytes); after the scan the pair holds (temp offset, final offset)
-__global__ void __launch_bounds__(1024) k_out_scan(unsigned long long *state, unsigned n_windows, unsigned long long *total_out) {
+__global__ void __launch_bounds__(1024) k_out_scan(unsigned long long *state, unsigned w_lo, unsigned w_hi, unsigned long long *total_io,
+                                                   unsigned long long *end_out) {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_carry;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) s_carry = *total_io;                         // bytes of the windows before w_lo (earlier launches of the batch)
     __syncthreads();
-    for (unsigned base = 0; base < n_windows; base += 1024) {
+    for (unsigned base = w_lo; base < w_hi; base += 1024) {
         const unsigned j = base + tid;
-        const unsigned long long v = j < n_windows ? state[2 + 2 * (size_t)j] : 0ull;
+        const unsigned long long v = j < w_hi ? state[2 + 2 * (size_t)j] : 0ull;
         unsigned long long x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -456,17 +457,17 @@ __global__ void __launch_bounds__(1024) k_out_scan(unsigned long long *state, un
         __syncthreads();
         unsigned long long add = s_carry;
         for (unsigned w = 0; w < warp; ++w) add += s_w[w];
-        if (j < n_windows) state[2 + 2 * (size_t)j] = x - v + add | (v << 40);       // final offset (40 bits) | bytes (24 bits)
+        if (j < w_hi) state[2 + 2 * (size_t)j] = x - v + add | (v << 40);            // final offset (40 bits) | bytes (24 bits)
         __syncthreads();
         if (tid == 1023) s_carry = add + x;
         __syncthreads();
     }
-    if (tid == 0) *total_out = s_carry;
+    if (tid == 0) { *total_io = s_carry; if (end_out) *end_out = s_carry; }
 }
 
-__global__ void __launch_bounds__(256) k_out_gather(const unsigned long long *__restrict__ state, unsigned n_windows,
+__global__ void __launch_bounds__(256) k_out_gather(const unsigned long long *__restrict__ state, unsigned w_lo, unsigned w_hi,
                                                     const unsigned char *__restrict__ tmp, unsigned char *__restrict__ out) {
-    for (unsigned j = blockIdx.x; j < n_windows; j += gridDim.x) {
+    for (unsigned j = w_lo + blockIdx.x; j < w_hi; j += gridDim.x) {
         const unsigned long long src = state[1 + 2 * (size_t)j], pk = state[2 + 2 * (size_t)j];
         const unsigned long long dst = pk & ((1ull << 40) - 1);
         const unsigned n2 = (unsigned)(pk >> 40) >> 1;                               // u16 units (all record sizes are even)

@@ -252,6 +252,8 @@ struct ChunkParams {
     uint64_t cap, n_items;
     int W, IW, k;
     unsigned CAPI, C, n_windows;
+    unsigned win_lo, win_hi;                 // windows of this launch (a batch is emitted in a few launches so that the D2H
+                                             // copy of one part overlaps the sort of the next)
     unsigned *ticket;
     const uint32_t *flags;
     const uint32_t *win_giant;

@@ -117,6 +117,7 @@ struct mgta_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr;
     std::vector<cudaEvent_t> ev_chunk;
+    std::vector<cudaEvent_t> ev_out;       // stage 2: one per part of a batch's output (D2H pipelined behind the sort)
     std::vector<uint64_t> chunk_end;       // end base of each chunk (multiples of 16384 except the last = total_bases)
     bool copy_pending = false;
     // mercy (need_mercy): candidates of the last stage 1 and the number of is_solid bits the per-read scan added
@@ -319,7 +320,7 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_hist, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_cursor, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_meta, NUM_BUCKETS * 3 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
-    if ((e = cudaMalloc(&ctx->d_totals, 16 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_totals, 32 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ec, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ec_bak, NUM_BUCKETS * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_ctr, CTR_COUNT * 4)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -344,6 +345,7 @@ extern "C" int mgta_ctx_create(const mgta_opts *opts, mgta_ctx **out) {
     if ((e = cudaHostAlloc(&ctx->h_hist2, ((size_t)1 << ctx->PB) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaMalloc(&ctx->d_xs, (size_t)(MAX_OWNERS + 1) * 24)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&ctx->h_pin, (2 * NUM_BUCKETS + 64) * 8, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    memset(ctx->h_pin, 0, (2 * NUM_BUCKETS + 64) * 8);
     if (opts->world > 1) {
         if (opts->world > MAX_OWNERS) { g_create_error = "at most 16 shards"; delete ctx; return MGTA_ERR_ARG; }
         const size_t small = (size_t)opts->world * (opts->world + 2) * 8;
@@ -369,6 +371,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     for (auto e : ctx->ev_chunk) cudaEventDestroy(e);
+    for (auto e : ctx->ev_out) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -2048,20 +2051,64 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         CP.aw = (pl.k - 1) >> 4; CP.ash = (15 - ((pl.k - 1) & 15)) * 2; CP.wpt = (2 * pl.k + 31) / 32;
         CP.out = tmpbuf; CP.out_cap = pl.out_cap; CP.state = state; CP.meta = ctx->d_meta; CP.totals = ctx->d_totals;
         CP.err = ctx->d_ctr + CTR_ERR;
-        const unsigned cgrid = std::min<unsigned>(n_windows, (unsigned)(ctx->sm_count * occ));
+        // The windows are sorted and emitted in a few launches.  With a sink, the bytes of part c go to the host on the copy
+        // stream while part c + 1 is sorted (a part's bytes are final and contiguous once its scan + gather ran).
+        const unsigned n_parts = sink ? std::max(1u, std::min(8u, n_windows / 2048u)) : 1u;
+        bool piped = sink && n_parts > 1 && ctx->h_out_bytes > 0;
+        if (piped && !ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        while (piped && ctx->ev_out.size() < n_parts) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_out.push_back(e);
+        }
+        unsigned long long *h_end = ctx->h_pin + 2 * NUM_BUCKETS + 16;                // [n_parts] running byte totals (pinned)
+        unsigned long long *d_end = ctx->d_totals + 16;                             // [8]
+        unsigned long long copied = 0;
+        auto retire = [&](unsigned c) -> int {                                      // part c has been enqueued: ship its bytes
+            if (!piped) return MGTA_OK;
+            cudaError_t qe;
+            while ((qe = cudaEventQuery(ctx->ev_out[c])) == cudaErrorNotReady) {}
+            if (qe != cudaSuccess) { ctx->err = std::string("stage 2 part event: ") + cudaGetErrorString(qe); return MGTA_ERR_CUDA; }
+            const unsigned long long end = h_end[c];
+            if (end > ctx->h_out_bytes) { piped = false; return MGTA_OK; }           // staging too small: one copy at the end
+            if (end > copied) {
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_out[c], 0));
+                CK(cudaMemcpyAsync(ctx->h_out + copied, outbuf + copied, end - copied, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                copied = end;
+            }
+            return MGTA_OK;
+        };
+        CK(cudaMemsetAsync(ctx->d_totals + 15, 0, 8, ctx->stream));
         if ((rc = begin_timed(ctx, PH_SORT))) return rc;
-        W_SWITCH(W, (k_sort_emit<WW><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP)));
-        // windows took their space in completion order: scan the byte counts and copy every window to its place in bucket order
-        k_out_scan<<<1, 1024, 0, ctx->stream>>>(state, n_windows, ctx->d_totals + 15);
-        k_out_gather<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(state, n_windows, tmpbuf, outbuf);
-        CK(cudaGetLastError());
+        for (unsigned c = 0; c < n_parts; ++c) {
+            CP.win_lo = (unsigned)((uint64_t)n_windows * c / n_parts);
+            CP.win_hi = (unsigned)((uint64_t)n_windows * (c + 1) / n_parts);
+            const unsigned cnt = CP.win_hi - CP.win_lo;
+            if (c) CK(cudaMemsetAsync(ctx->d_ctr + CTR_TICKET, 0, 4, ctx->stream));
+            const unsigned cgrid = std::max(1u, std::min<unsigned>(cnt, (unsigned)(ctx->sm_count * occ)));
+            W_SWITCH(W, (k_sort_emit<WW><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP)));
+            // windows took their space in completion order: scan the byte counts and copy every window to its place in bucket order
+            k_out_scan<<<1, 1024, 0, ctx->stream>>>(state, CP.win_lo, CP.win_hi, ctx->d_totals + 15, d_end + c);
+            k_out_gather<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(state, CP.win_lo, CP.win_hi, tmpbuf, outbuf);
+            CK(cudaGetLastError());
+            st->n_launches += 3;
+            if (piped) {
+                CK(cudaMemcpyAsync(h_end + c, d_end + c, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaEventRecord(ctx->ev_out[c], ctx->stream));
+                if (c >= 1 && (rc = retire(c - 1))) return rc;
+            }
+        }
         if ((rc = end_timed(ctx))) return rc;
-        st->n_launches += 3;
         // ---- batch epilogue: error flags, output
         unsigned *h_ctr = reinterpret_cast<unsigned *>(ctx->h_pin + 2 * NUM_BUCKETS);
         unsigned long long *h_state = ctx->h_pin + 2 * NUM_BUCKETS + 8;
         CK(cudaMemcpyAsync(h_ctr, ctx->d_ctr, CTR_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_state, ctx->d_totals + 15, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (sink) {
+            meta_host.resize((size_t)(b1 - b0) * 3);
+            CK(cudaMemcpyAsync(meta_host.data(), ctx->d_meta + (size_t)b0 * 3, (size_t)(b1 - b0) * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (piped && (rc = retire(n_parts - 1))) return rc;
         CK(mgta_stream_wait(ctx->stream));
         st->n_giants += h_ctr[CTR_NGIANTS] + h_ctr[CTR_NOVF];      // windows sorted by the LSD passes (low-complexity or forced)
         const unsigned dev_err = h_ctr[CTR_ERR];
@@ -2069,16 +2116,20 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         const unsigned long long bytes = *h_state;
         st->out_bytes += bytes;
         if (sink) {
-            if (bytes > ctx->h_out_bytes) {
-                cudaFreeHost(ctx->h_out);
-                ctx->h_out = nullptr; ctx->h_out_bytes = 0;
-                CK(cudaHostAlloc(&ctx->h_out, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
-                ctx->h_out_bytes = bytes + bytes / 4 + 4096;
+            if (piped && copied == bytes) {
+                CK(mgta_stream_wait(ctx->copy_stream));
+            } else {
+                if (ctx->copy_stream) CK(mgta_stream_wait(ctx->copy_stream));
+                if (bytes > ctx->h_out_bytes) {
+                    cudaFreeHost(ctx->h_out);
+                    ctx->h_out = nullptr; ctx->h_out_bytes = 0;
+                    CK(cudaHostAlloc(&ctx->h_out, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+                    ctx->h_out_bytes = bytes + bytes / 4 + 4096;
+                    copied = 0;
+                }
+                if (bytes > copied) CK(cudaMemcpyAsync(ctx->h_out + copied, outbuf + copied, bytes - copied, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(mgta_stream_wait(ctx->stream));
             }
-            meta_host.resize((size_t)(b1 - b0) * 3);
-            if (bytes) CK(cudaMemcpyAsync(ctx->h_out, outbuf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(meta_host.data(), ctx->d_meta + (size_t)b0 * 3, (size_t)(b1 - b0) * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(mgta_stream_wait(ctx->stream));
             if (sink(user, b0, b1, ctx->h_out, bytes, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
         }
         b0 = b1;

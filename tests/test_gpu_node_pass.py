@@ -39,3 +39,25 @@ def test_node_pass_gives_the_same_records_from_fewer_items(read_lib, ds, k, m, k
     if ds == "meta200k" and not kw:
         assert a["stats"]["n_items"] * 2 < b["stats"]["n_items"]       # one item per record instead of ~3
         assert a["stats"]["n_tip_items"] == 2 * int(a["meta"][:, 1].sum())   # every tip k-mer: one $-in and one $-out item
+
+
+def test_stage2_output_delivered_in_parts_behind_the_sort(golden, read_lib):
+    """With a sink, a batch is sorted and emitted in a few launches and the bytes of one part travel to the host while the
+    next part is sorted (from the second delivery on, once the pinned staging buffer exists).  Same bytes either way."""
+    g = golden["cases"]["meta1m_k31_m2"]
+    _, rd = read_lib(g["dataset"])
+    from oracle import oracle as O
+    with cabi.Context(g["k"], g["m"]) as ctx:
+        ctx.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+        ctx.stage1()
+        first = ctx.stage2()
+        launches_first = ctx.stats(2)["n_launches"]
+        second = ctx.stage2()                              # pipelined delivery
+        nbytes, meta3, _ = ctx.stage2(collect="count")
+        dev_only = ctx.stage2(collect=False)
+        launches_dev = ctx.stats(2)["n_launches"]
+    assert O.stream_hash(first[0]) == g["stream_hash"] and O.meta_hash(first[1]) == g["meta_hash"]
+    assert second[0] == first[0] and np.array_equal(second[1], first[1]) and np.array_equal(second[2], first[2])
+    assert nbytes == len(first[0]) and np.array_equal(meta3, first[1])
+    assert np.array_equal(dev_only[2], first[2])
+    assert launches_first > launches_dev                   # several sort launches with a sink, one without
