@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--total-reads", type=int, default=0,
                     help="strong scaling: this many reads in all, split over the GPUs (0 = weak scaling with --reads-per-gpu each)")
     ap.add_argument("--genomes", type=int, default=0, help="genomes of the community (0 = --genomes-per-gpu x GPUs; strong scaling: x total/20M)")
+    ap.add_argument("--gen-chunk", type=int, default=1_000_000,
+                    help="reads per RNG chunk of the generator (reads per GPU must be a multiple; the read set depends on it)")
     ap.add_argument("--no-hash", action="store_true", help="skip the (untimed) parity hashes of the GPU output")
     ap.add_argument("--full-reference", action="store_true",
                     help="N=1: also build the WHOLE workload with the reference on the host cores (untimed) and compare the hashes")
@@ -55,7 +57,7 @@ def parse():
                     help="N>1: rank 0 uploads all reads and broadcasts them (default: every rank uploads its slice, NCCL all-gather)")
     a = ap.parse_args()
     if a.total_reads:
-        assert a.total_reads % (a.gpus * 1_000_000) == 0, "--total-reads must be a multiple of 1M x GPUs"
+        assert a.total_reads % (a.gpus * a.gen_chunk) == 0, "--total-reads must be a multiple of --gen-chunk x GPUs"
         a.reads_per_gpu = a.total_reads // a.gpus
     return a
 
@@ -113,7 +115,7 @@ def write_sample(a, work):
     from megagta_b200 import synth
     n = auto_sample(a)
     prefix = os.path.join(work, "sample")
-    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n, n_genomes=sample_genomes(a))
+    synth.packed_metagenome(n, a.read_len, seed=a.seed, bin_prefix=prefix, bin_reads=n, n_genomes=sample_genomes(a), chunk=a.gen_chunk)
     return prefix, n
 
 
@@ -312,7 +314,7 @@ def main():
     # place in the full device buffer, and one NCCL all-gather over NVLink completes the buffers on every GPU.
     sharded_upload = world > 1 and not a.root_upload
     per_words = a.reads_per_gpu * L // 16                      # words of one shard's slice (reads_per_gpu * L % 16 == 0)
-    assert not sharded_upload or (a.reads_per_gpu * L) % 16 == 0 and a.reads_per_gpu % 1_000_000 == 0
+    assert not sharded_upload or (a.reads_per_gpu * L) % 16 == 0 and a.reads_per_gpu % a.gen_chunk == 0
     # Pinned staging buffers should live on the NUMA node the GPU hangs off (first touch follows the thread): bind this
     # process to the GPU's CPUs (NVML) while it allocates and runs the GPU arm; the CPU baseline gets all cores back.
     full_affinity = os.sched_getaffinity(0)
@@ -335,13 +337,14 @@ def main():
     if sharded_upload:
         seq, start = synth.packed_metagenome(a.reads_per_gpu, L, seed=a.seed, first_read=rank * a.reads_per_gpu, n_genomes=n_genomes(a, world),
                                              bin_prefix=sample_prefix if rank == 0 else None, bin_reads=sample_n if rank == 0 else 0,
-                                             procs=max(1, (os.cpu_count() or 8) // world))
+                                             procs=max(1, (os.cpu_count() or 8) // world), chunk=a.gen_chunk)
         seq_pin = torch.from_numpy(seq[:per_words].view(np.int32)).pin_memory()
         start_pin = torch.from_numpy((start[:a.reads_per_gpu] + np.uint64(rank * a.reads_per_gpu * L)).view(np.int64)).pin_memory()
         del seq, start
     elif rank == 0:
         seq, start = synth.packed_metagenome(n_reads, L, seed=a.seed, bin_prefix=sample_prefix,
-                                             bin_reads=n_reads if (a.full_reference and world == 1) else sample_n, n_genomes=n_genomes(a, world))
+                                             bin_reads=n_reads if (a.full_reference and world == 1) else sample_n, n_genomes=n_genomes(a, world),
+                                             chunk=a.gen_chunk)
         seq_pin = torch.from_numpy(seq).pin_memory()
         start_pin = torch.from_numpy(start.view(np.int64)).pin_memory()
         del seq, start
@@ -519,13 +522,14 @@ def main():
         top = kern[0]
         ach = top[2] / (top[1] / 1000.0) / 1e9 if top[1] > 0 else 0.0
         step_bytes = sum(k[2] for k in kern)
-        traffic = None                                 # DRAM bytes of one launch from the committed ncu capture, same configuration only
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_s8_traffic.json")))
+        traffic = None                                 # DRAM bytes of the kernel from the committed ncu capture, same configuration only
+        try:                                           # profiles/traffic.json is generated by tools/ncu_traffic.py, never by hand
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             c = tr["config"]
-            if (tr["kernel"] == top[0] and n_gpus == c["n_gpus"] and n_reads == c["reads"] and L == c["read_len"] and a.k == c["k"]
-                    and a.m == c["min_count"] and n2 == tr["items"]):
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            if (n_gpus == c["n_gpus"] and n_reads == c["reads"] and L == c["read_len"] and a.k == c["k"] and a.m == c["min_count"]
+                    and n1 == tr["s1_items"] and n2 == tr["s2_items"] and top[0] in tr["kernels"]):
+                e = tr["kernels"][top[0]]
+                traffic = e["dram_bytes_read"] + e["dram_bytes_write"]
         except Exception:
             traffic = None
         roofline = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
