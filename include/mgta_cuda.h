@@ -207,6 +207,53 @@ int mgta_get_stats(mgta_ctx *ctx, int stage /*1|2*/, mgta_stage_stats *out);
 int mgta_words_per_key(int stage, int kmer_k);
 int mgta_abi_version(void);
 
+/* ---- SdBG load + rank/select build on the device -----------------------------------------------------
+ * Replaces SuccinctDBG::LoadFromMultiFile (reference succinct_dbg.cpp:595-723: a serial u16-at-a-time loop over the whole
+ * record stream), SuccinctDBG::init (succinct_dbg.h:62-83) and the table builds RankAndSelect4Bits::Build
+ * (rank_and_select.h:81-150) / RankAndSelect1Bit::Build (rank_and_select.h:420-487).  The builder eats the stage-2
+ * deliveries (mgta_sdbg_sink has the mgta_bucket_sink signature; `bytes` may also be a DEVICE pointer, so a stream that
+ * is still in HBM never visits the host) or the bucket ranges of <prefix>.sdbg.<i> files, and leaves every array of the
+ * in-memory graph on the device in the reference's own layout, bit for bit:
+ *   w (4 bits per edge, 16 per u64), last / is_tip / invalid (= is_tip | W == 0) / is_multi_1 (bit vectors, 64 per u64),
+ *   edge_multi (u8 per edge; 255 = see the large list) + (edge, multiplicity) pairs of the large multiplicities in edge
+ *   order (the reference keeps them in a khash; its alternative u16-per-edge array for graphs with > 8 % large
+ *   multiplicities is the same information), tip_node_seq, f / rank_f, and the sampled rank (major i64 every 65536 +
+ *   minor u16 every 256) and select (interval of every 256th occurrence) tables of W per character, of last and of is_tip.
+ * need_multiplicity mirrors LoadFromMultiFile's flag: 1 -> edge_multi + large list, 0 -> is_multi_1. */
+typedef struct mgta_sdbg mgta_sdbg;
+
+typedef struct {
+    int64_t size;                  /* edges (total_size of sdbg_info) */
+    int32_t kmer_k, words_per_tip_label;
+    int64_t num_tips, num_large_mul;
+    int64_t f[6], rank_f[6];       /* SdbgReader::read_info f_ (sdbg_multi_io.h:253-268); rank_f = ones of last before f[i] */
+    int64_t w_freq[9];             /* RankAndSelect4Bits::char_frequency */
+    int64_t last_ones, tip_ones;   /* RankAndSelect1Bit::total_num_ones */
+    int64_t n_minor, n_major;      /* entries of every minor / major table */
+} mgta_sdbg_header_t;
+
+typedef enum {
+    MGTA_SDBG_W = 0, MGTA_SDBG_LAST = 1, MGTA_SDBG_IS_TIP = 2, MGTA_SDBG_INVALID = 3, MGTA_SDBG_IS_MULTI_1 = 4,
+    MGTA_SDBG_EDGE_MULTI = 5, MGTA_SDBG_LARGE_EDGE = 6 /* u64 */, MGTA_SDBG_LARGE_VALUE = 7 /* u16 */, MGTA_SDBG_TIP_SEQ = 8,
+    /* tables (after mgta_sdbg_finish); W_* take the character c in [0, 9) */
+    MGTA_SDBG_W_MINOR = 16, MGTA_SDBG_W_MAJOR = 17, MGTA_SDBG_W_SELECT = 18, MGTA_SDBG_LAST_MINOR = 19, MGTA_SDBG_LAST_MAJOR = 20,
+    MGTA_SDBG_LAST_SELECT = 21, MGTA_SDBG_TIP_MINOR = 22, MGTA_SDBG_TIP_MAJOR = 23
+} mgta_sdbg_array_id;
+
+int mgta_sdbg_create(int device, void *stream /* cudaStream_t or NULL */, int kmer_k, int need_multiplicity, mgta_sdbg **out);
+void mgta_sdbg_destroy(mgta_sdbg *g);
+const char *mgta_sdbg_last_error(const mgta_sdbg *g);
+/* records of buckets [bucket_begin, bucket_end) in bucket order, deliveries in ascending order starting at bucket 0;
+ * bytes: host or device; meta: host, 3 int64 per bucket (num_items, num_tips, num_large_mul) */
+int mgta_sdbg_append(mgta_sdbg *g, int32_t bucket_begin, int32_t bucket_end, const void *bytes, uint64_t n_bytes, const int64_t *meta);
+int mgta_sdbg_sink(void *sdbg, int32_t bucket_begin, int32_t bucket_end, const void *bytes, uint64_t n_bytes, const int64_t *meta);
+int mgta_sdbg_finish(mgta_sdbg *g);            /* rank / select tables, f, rank_f */
+int mgta_sdbg_header(const mgta_sdbg *g, mgta_sdbg_header_t *h);
+int mgta_sdbg_array(mgta_sdbg *g, int which, int c, const void **dev_ptr, uint64_t *n_bytes);
+int mgta_sdbg_copy(mgta_sdbg *g, int which, int c, void *host, uint64_t n_bytes);
+/* Stage 2 straight into the builder: the records of every batch are parsed where they lie in HBM (no D2H, no sink). */
+int mgta_stage2_into_sdbg(mgta_ctx *ctx, mgta_sdbg *g, int64_t *totals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,7 +49,23 @@ EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_r
            "mgta_reads_device_buffers", "mgta_stage1_histogram",
            "mgta_stage2_histogram", "mgta_stage1", "mgta_solid_device_buffer", "mgta_get_is_solid", "mgta_set_is_solid",
            "mgta_get_mercy_candidates", "mgta_get_num_mercy", "mgta_stage2", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
-           "mgta_abi_version", "mgta_sharded_begin", "mgta_sharded_step", "mgta_sharded_result"]
+           "mgta_abi_version", "mgta_sharded_begin", "mgta_sharded_step", "mgta_sharded_result",
+           "mgta_sdbg_create", "mgta_sdbg_destroy", "mgta_sdbg_last_error", "mgta_sdbg_append", "mgta_sdbg_sink", "mgta_sdbg_finish",
+           "mgta_sdbg_header", "mgta_sdbg_array", "mgta_sdbg_copy", "mgta_stage2_into_sdbg"]
+
+
+class SdbgHeader(ctypes.Structure):
+    """mgta_sdbg_header_t"""
+    _fields_ = [("size", ctypes.c_int64), ("kmer_k", ctypes.c_int32), ("words_per_tip_label", ctypes.c_int32),
+                ("num_tips", ctypes.c_int64), ("num_large_mul", ctypes.c_int64), ("f", ctypes.c_int64 * 6), ("rank_f", ctypes.c_int64 * 6),
+                ("w_freq", ctypes.c_int64 * 9), ("last_ones", ctypes.c_int64), ("tip_ones", ctypes.c_int64),
+                ("n_minor", ctypes.c_int64), ("n_major", ctypes.c_int64)]
+
+
+(SDBG_W, SDBG_LAST, SDBG_IS_TIP, SDBG_INVALID, SDBG_IS_MULTI_1, SDBG_EDGE_MULTI, SDBG_LARGE_EDGE, SDBG_LARGE_VALUE,
+ SDBG_TIP_SEQ) = range(9)
+(SDBG_W_MINOR, SDBG_W_MAJOR, SDBG_W_SELECT, SDBG_LAST_MINOR, SDBG_LAST_MAJOR, SDBG_LAST_SELECT, SDBG_TIP_MINOR,
+ SDBG_TIP_MAJOR) = range(16, 24)
 
 _lib = None
 
@@ -89,6 +105,18 @@ def load():
         lib.mgta_sharded_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, SINK, ctypes.c_void_p]
         lib.mgta_sharded_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(Collective)]
         lib.mgta_sharded_result.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_sdbg_create.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        lib.mgta_sdbg_destroy.argtypes = [ctypes.c_void_p]
+        lib.mgta_sdbg_destroy.restype = None
+        lib.mgta_sdbg_last_error.argtypes = [ctypes.c_void_p]
+        lib.mgta_sdbg_last_error.restype = ctypes.c_char_p
+        lib.mgta_sdbg_append.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        lib.mgta_sdbg_finish.argtypes = [ctypes.c_void_p]
+        lib.mgta_sdbg_header.argtypes = [ctypes.c_void_p, ctypes.POINTER(SdbgHeader)]
+        lib.mgta_sdbg_array.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                        ctypes.POINTER(ctypes.c_uint64)]
+        lib.mgta_sdbg_copy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64]
+        lib.mgta_stage2_into_sdbg.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -270,3 +298,61 @@ class Context:
         s = StageStats()
         self._check(self.lib.mgta_get_stats(self.h, stage, ctypes.byref(s)), "mgta_get_stats")
         return s.as_dict()
+
+
+class Sdbg:
+    """The in-memory succinct de Bruijn graph (SuccinctDBG::LoadFromMultiFile + rank/select tables) built on the device:
+    thin wrapper over mgta_sdbg_* (include/mgta_cuda.h)."""
+
+    def __init__(self, k, need_multiplicity=True, device=0, stream=None):
+        self.lib = load()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.mgta_sdbg_create(device, stream, k, int(need_multiplicity), ctypes.byref(self.h))
+        if rc != 0:
+            raise MgtaError("mgta_sdbg_create failed (%d): no CUDA device? (there is no CPU fallback)" % rc)
+        self.need_multiplicity = bool(need_multiplicity)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MgtaError("%s failed (%d): %s" % (what, rc, self.lib.mgta_sdbg_last_error(self.h).decode()))
+
+    def close(self):
+        if self.h:
+            self.lib.mgta_sdbg_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def append(self, b0, b1, stream_bytes, meta):
+        """records of buckets [b0, b1) (bytes-like, host) + their int64[b1 - b0, 3] table"""
+        meta = np.ascontiguousarray(meta, dtype=np.int64)
+        buf = np.frombuffer(stream_bytes, dtype=np.uint8) if len(stream_bytes) else np.zeros(0, np.uint8)
+        self._check(self.lib.mgta_sdbg_append(self.h, b0, b1, _p(buf) if len(buf) else None, len(buf), _p(meta)), "mgta_sdbg_append")
+
+    def from_stage2(self, ctx):
+        """stage 2 of `ctx` straight into the builder (records parsed in HBM) -> totals int64[10]"""
+        totals = np.zeros(10, dtype=np.int64)
+        rc = self.lib.mgta_stage2_into_sdbg(ctx.h, self.h, _p(totals))
+        if rc != 0:
+            raise MgtaError("mgta_stage2_into_sdbg failed (%d): %s" % (rc, self.lib.mgta_last_error(ctx.h).decode()))
+        return totals
+
+    def finish(self):
+        self._check(self.lib.mgta_sdbg_finish(self.h), "mgta_sdbg_finish")
+        return self.header()
+
+    def header(self):
+        h = SdbgHeader()
+        self._check(self.lib.mgta_sdbg_header(self.h, ctypes.byref(h)), "mgta_sdbg_header")
+        return h
+
+    def array(self, which, c=0, dtype=np.uint8):
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self.lib.mgta_sdbg_array(self.h, which, c, ctypes.byref(p), ctypes.byref(n)), "mgta_sdbg_array")
+        out = np.zeros(n.value, dtype=np.uint8)
+        self._check(self.lib.mgta_sdbg_copy(self.h, which, c, _p(out), n.value), "mgta_sdbg_copy")
+        return out.view(dtype)

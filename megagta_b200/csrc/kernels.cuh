@@ -32,6 +32,8 @@ enum { ERR_NEXT_LIST_FULL = 1, ERR_GIANT_LIST_FULL = 2, ERR_CHUNK_TOO_BIG = 4, E
 struct WalkParams {
     const uint32_t *seq;
     const uint64_t *start;
+    const uint32_t *lut;            // read lookup table (k_build_read_lut)
+    uint64_t n_lut;
     uint64_t n_reads, n_short, total_bases;
     int k, all_solid;
     const uint32_t *solid;          // stage 2: one bit per base position (edge offset o of read r <=> start[r]+o)
@@ -52,6 +54,26 @@ __device__ __forceinline__ uint64_t find_read(const uint64_t *__restrict__ start
     return lo;
 }
 
+// Read lookup table (the device counterpart of SequencePackage::pos_to_id_, sequence_package.h:145-188):
+// lut[i] = largest r with start[r] <= i * 1024, for i in [0, (total_bases >> 10) + 2).  A CTA tile reads two entries
+// instead of running two binary searches over all of start_idx with dependent global loads (measured: 42 % of the stall
+// samples of k_edge_part sat on the barrier behind those searches).
+constexpr int READ_LUT_SHIFT = 10;
+
+__global__ void __launch_bounds__(256) k_build_read_lut(const uint64_t *__restrict__ start, uint64_t n_reads, uint64_t n_lut, uint32_t *lut) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n_lut) lut[i] = (uint32_t)find_read(start, 0, n_reads - 1, i << READ_LUT_SHIFT);
+}
+
+// reads of the tile [g0, gend): r_lo = the read of base g0 (exact when g0 is a multiple of 1024, else a lower bound),
+// r_hi >= the read of base gend - 1
+__device__ __forceinline__ void tile_read_span(const uint32_t *__restrict__ lut, uint64_t n_lut, uint64_t g0, uint64_t gend,
+                                               uint64_t &r_lo, uint64_t &r_hi) {
+    r_lo = __ldg(lut + (g0 >> READ_LUT_SHIFT));
+    const uint64_t j = (gend + ((1u << READ_LUT_SHIFT) - 1)) >> READ_LUT_SHIFT;
+    r_hi = __ldg(lut + (j < n_lut - 1 ? j : n_lut - 1));
+}
+
 __device__ __forceinline__ bool bit_at(const uint32_t *__restrict__ bits, uint64_t i) {
     return (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
 }
@@ -59,7 +81,6 @@ __device__ __forceinline__ bool bit_at(const uint32_t *__restrict__ bits, uint64
 template <int W, int STAGE, int MODE>
 __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams P) {
     __shared__ __align__(16) uint32_t sw[WALK_SMEM_WORDS];
-    __shared__ uint64_t s_r[2];
     const uint64_t g0 = (uint64_t)blockIdx.x * WALK_TILE;
     const uint64_t gend = min(g0 + (uint64_t)WALK_TILE, P.total_bases);
     const uint64_t w_lo = (g0 >> 4) >= WALK_BACK_WORDS ? (g0 >> 4) - WALK_BACK_WORDS : 0;
@@ -69,10 +90,9 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams P) {
         uint4 *dst = reinterpret_cast<uint4 *>(sw);
         for (int i = threadIdx.x; i < WALK_SMEM_WORDS / 4; i += WALK_THREADS) dst[i] = __ldg(src + i);
     }
-    if (threadIdx.x == 0) s_r[0] = find_read(P.start, 0, P.n_reads - 1, g0);
-    if (threadIdx.x == 32) s_r[1] = find_read(P.start, 0, P.n_reads - 1, gend - 1);
+    uint64_t r_lo, r_hi;
+    tile_read_span(P.lut, P.n_lut, g0, gend, r_lo, r_hi);
     __syncthreads();
-    const uint64_t r_lo = s_r[0], r_hi = s_r[1];
     const int k = P.k;
     unsigned n_dollar = 0;
 #pragma unroll 1

@@ -22,6 +22,8 @@ constexpr uint32_t S1_FLAG_MASK = ~63u;          // key without head<<3|tail (s1
 struct CtxPartParams {
     const uint32_t *seq;
     const uint64_t *start;
+    const uint32_t *lut;              // read lookup table (k_build_read_lut)
+    uint64_t n_lut;
     uint64_t n_reads, n_short, total_bases;
     int k;
     int sh1, sh2;
@@ -41,7 +43,6 @@ __global__ void __launch_bounds__(PART_THREADS) k_ctx_part(const CtxPartParams P
     constexpr int IW = W + 2, SLOTS = 2 * TP;
     constexpr int SW_WORDS = TP / 16 + WALK_BACK_WORDS + 12;
     __shared__ __align__(16) uint32_t sw[SW_WORDS];
-    __shared__ uint64_t s_r[2];
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, SLOTS);
     const int tid = threadIdx.x;
@@ -56,10 +57,9 @@ __global__ void __launch_bounds__(PART_THREADS) k_ctx_part(const CtxPartParams P
     }
     for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
     for (int i = tid; i < SLOTS; i += PART_THREADS) S.bin[i] = 0xFFFFu;
-    if (tid == 0) s_r[0] = find_read(P.start, 0, P.n_reads - 1, g0);
-    if (tid == 32) s_r[1] = find_read(P.start, 0, P.n_reads - 1, gend - 1);
+    uint64_t r_lo, r_hi;
+    tile_read_span(P.lut, P.n_lut, g0, gend, r_lo, r_hi);
     __syncthreads();
-    const uint64_t r_lo = s_r[0], r_hi = s_r[1];
     const unsigned sub_mask = (1u << P.lb2) - 1u;
     for (int i = tid; i < TP; i += PART_THREADS) {
         const uint64_t g = g0 + (uint64_t)i;

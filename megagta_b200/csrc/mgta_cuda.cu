@@ -71,6 +71,10 @@ struct mgta_ctx {
     int max_len = 0;
     uint32_t *d_solid = nullptr;
     uint64_t solid_words = 0;
+    bool sink_device = false;              // stage 2 hands the sink DEVICE pointers (mgta_stage2_into_sdbg): no D2H of the records
+    uint32_t *d_lut = nullptr;             // read lookup table (k_build_read_lut), built on first use after the reads change
+    uint64_t n_lut = 0;
+    bool lut_valid = false;
     // small device state
     unsigned long long *d_hist = nullptr, *d_cursor = nullptr, *d_meta = nullptr, *d_totals = nullptr, *d_ec = nullptr, *d_ec_bak = nullptr;
     unsigned *d_ctr = nullptr;
@@ -360,7 +364,7 @@ extern "C" void mgta_ctx_destroy(mgta_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->opt.device);
     mgta_stream_wait(ctx->stream);
-    cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
+    cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid); cudaFree(ctx->d_lut);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_cursor); cudaFree(ctx->d_meta); cudaFree(ctx->d_totals); cudaFree(ctx->d_ec); cudaFree(ctx->d_ec_bak);
     cudaFree(ctx->d_ctr); cudaFree(ctx->arena); cudaFree(ctx->d_edges); cudaFree(ctx->d_hist_s2);
     cudaFree(ctx->d_xs); cudaFree(ctx->d_cand); cudaFree(ctx->d_tips); cudaFree(ctx->d_hist_bak);
@@ -391,6 +395,7 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     if (total == 0) FAIL(MGTA_ERR_ARG, "reads: no bases");
     if (n_words * 16 < total) FAIL(MGTA_ERR_ARG, "reads: packed_seq shorter than start_idx says");
     if (total >= (1ull << 40) - 1) FAIL(MGTA_ERR_ARG, "reads: more than 2^40 bases");
+    if (n_reads >= 0xFFFFFFFFull) FAIL(MGTA_ERR_ARG, "reads: more than 2^32 - 2 reads");
     CK(cudaSetDevice(ctx->opt.device));
     if (ctx->copy_pending) {                                       // a previous asynchronous upload still owns the buffers
         CK(cudaStreamSynchronize(ctx->copy_stream));
@@ -399,11 +404,12 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     const uint64_t padded = ((n_words + 3) & ~3ull) + SEQ_PAD_WORDS;
     const uint64_t solid_words = (total + 31) / 32 + 4;
     if (n_words != ctx->n_words || n_reads != ctx->n_reads || total != ctx->total_bases || !ctx->d_seq) {     // reuse buffers of equal shape
-        cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid);
-        ctx->d_seq = nullptr; ctx->d_start = nullptr; ctx->d_solid = nullptr;
+        cudaFree(ctx->d_seq); cudaFree(ctx->d_start); cudaFree(ctx->d_solid); cudaFree(ctx->d_lut);
+        ctx->d_seq = nullptr; ctx->d_start = nullptr; ctx->d_solid = nullptr; ctx->d_lut = nullptr;
         CK(cudaMalloc(&ctx->d_seq, padded * 4));
         CK(cudaMalloc(&ctx->d_start, (n_reads + 1) * 8));
         CK(cudaMalloc(&ctx->d_solid, solid_words * 4));
+        CK(cudaMalloc(&ctx->d_lut, ((total >> READ_LUT_SHIFT) + 2) * 4));
         ctx->budget_cached = 0;
     }
     ctx->solid_words = solid_words;
@@ -416,8 +422,21 @@ int alloc_reads(mgta_ctx *ctx, uint64_t n_words, uint64_t n_reads, uint64_t n_sh
     ctx->solid_valid = false;
     ctx->stage1_done = false;
     ctx->n_positions_valid = false;
+    ctx->n_lut = (total >> READ_LUT_SHIFT) + 2;
+    ctx->lut_valid = false;
     ctx->xch.valid = false;
     ctx->slab_suggest = 0;
+    return MGTA_OK;
+}
+
+// the read lookup table of the current start_idx (start_idx has landed on the device or its copy is ordered before
+// ev_start); every kernel that walks base positions takes it
+int ensure_read_lut(mgta_ctx *ctx) {
+    if (ctx->lut_valid) return MGTA_OK;
+    if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_start, 0));
+    k_build_read_lut<<<(unsigned)((ctx->n_lut + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_reads, ctx->n_lut, ctx->d_lut);
+    CK(cudaGetLastError());
+    ctx->lut_valid = true;
     return MGTA_OK;
 }
 }  // namespace
@@ -493,7 +512,7 @@ namespace {
 WalkParams walk_params(mgta_ctx *ctx) {
     WalkParams P;
     memset(&P, 0, sizeof(P));
-    P.seq = ctx->d_seq; P.start = ctx->d_start; P.n_reads = ctx->n_reads; P.n_short = ctx->n_short;
+    P.seq = ctx->d_seq; P.start = ctx->d_start; P.lut = ctx->d_lut; P.n_lut = ctx->n_lut; P.n_reads = ctx->n_reads; P.n_short = ctx->n_short;
     P.total_bases = ctx->total_bases; P.k = ctx->opt.kmer_k; P.all_solid = ctx->opt.min_count == 1;
     P.solid = ctx->d_solid; P.hist = ctx->d_hist; P.cursor = ctx->d_cursor; P.n_dollar = ctx->d_totals + 12;
     P.b_lo = 0; P.b_hi = NUM_BUCKETS;
@@ -520,6 +539,7 @@ int histogram(mgta_ctx *ctx, int stage, mgta_stage_stats *st) {
     if (!ctx->d_seq) FAIL(MGTA_ERR_STATE, "no reads: call mgta_set_reads first");
     CK(cudaSetDevice(ctx->opt.device));
     { int rcw = wait_reads(ctx); if (rcw) return rcw; }
+    { int rcl = ensure_read_lut(ctx); if (rcl) return rcl; }
     const int W = stage == 1 ? key_words_s1(ctx->opt.kmer_k) : key_words_s2(ctx->opt.kmer_k);
     WalkParams P = walk_params(ctx);
     const unsigned grid = (unsigned)((ctx->total_bases + WALK_TILE - 1) / WALK_TILE);
@@ -617,6 +637,7 @@ int ensure_arena(mgta_ctx *ctx, size_t bytes) {
 }
 
 int count_positions(mgta_ctx *ctx) {
+    { int rcl = ensure_read_lut(ctx); if (rcl) return rcl; }
     if (ctx->n_positions_valid) return MGTA_OK;
     if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_start, 0));     // start_idx has landed; packed_seq may not have
     CK(cudaMemsetAsync(ctx->d_totals + 13, 0, 8, ctx->stream));
@@ -768,7 +789,7 @@ int launch_scans(mgta_ctx *ctx, const ScanParams &SP) {
 }
 
 int launch_split(mgta_ctx *ctx, const SplitParams &SP) {
-    const size_t smem = bin_smem_bytes(SP.IW, (int)SP.T);
+    const size_t smem = bin_smem_bytes(SP.IW, (int)SP.T + 4);      // + 4: the bulk copy of a chunk starts on a 16-byte boundary
     CK(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_split, PART_THREADS, smem));
@@ -1047,7 +1068,7 @@ int run_count(mgta_ctx *ctx, CountMode mode, mgta_stage_stats *st) {
             // ---- K1+K2: extraction + level-1 hash partition
             EdgePartParams EP;
             memset(&EP, 0, sizeof(EP));
-            EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
+            EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.lut = ctx->d_lut; EP.n_lut = ctx->n_lut; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
             EP.total_bases = ctx->total_bases; EP.k = k; EP.g_begin = 0; EP.g_end = ctx->total_bases;
             EP.filter = cp.stage1_mode ? 0 : 1; EP.all_solid = ctx->opt.min_count == 1; EP.solid = ctx->d_solid;
             EP.sh1 = 32 - (int)cp.lb1; EP.sh2 = 32 - cp.bits; EP.lb2 = cp.lb2; EP.b_lo = b_lo; EP.b_hi = b_hi;
@@ -1170,7 +1191,7 @@ int exchange_scan(mgta_ctx *ctx, uint64_t r_begin, uint64_t r_end, uint64_t slab
         if (g_begin < g_end) {
             EdgePartParams EP;
             memset(&EP, 0, sizeof(EP));
-            EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
+            EP.seq = ctx->d_seq; EP.start = ctx->d_start; EP.lut = ctx->d_lut; EP.n_lut = ctx->n_lut; EP.n_reads = ctx->n_reads; EP.n_short = ctx->n_short;
             EP.total_bases = ctx->total_bases; EP.k = cp.k; EP.filter = 0; EP.all_solid = 0; EP.solid = ctx->d_solid;
             EP.sh1 = 32 - (int)cp.lb1; EP.sh2 = 32 - cp.bits; EP.lb2 = cp.lb2; EP.b_lo = 0; EP.b_hi = cp.B1;
             EP.cursor1 = cur; EP.slab_cap = slab_items; EP.slab_stride = stride; EP.hist2 = nullptr;
@@ -1377,7 +1398,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
             CK(cudaGetLastError());
             CtxPartParams XP0;
             memset(&XP0, 0, sizeof(XP0));
-            XP0.seq = ctx->d_seq; XP0.start = ctx->d_start; XP0.n_reads = ctx->n_reads; XP0.n_short = ctx->n_short;
+            XP0.seq = ctx->d_seq; XP0.start = ctx->d_start; XP0.lut = ctx->d_lut; XP0.n_lut = ctx->n_lut; XP0.n_reads = ctx->n_reads; XP0.n_short = ctx->n_short;
             XP0.total_bases = ctx->total_bases; XP0.k = k; XP0.sh1 = 32 - (int)lb1; XP0.sh2 = 32 - bits; XP0.lb2 = lb2;
             XP0.b_lo = b_lo; XP0.b_hi = b_hi; XP0.cursor1 = cur1; XP0.slab_cap = L.slab_cap; XP0.hist2 = hist2; XP0.dst = bufA;
             XP0.cap = L.capA; XP0.err = ctx->d_ctr + CTR_ERR;
@@ -2053,7 +2074,7 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         CP.err = ctx->d_ctr + CTR_ERR;
         // The windows are sorted and emitted in a few launches.  With a sink, the bytes of part c go to the host on the copy
         // stream while part c + 1 is sorted (a part's bytes are final and contiguous once its scan + gather ran).
-        const unsigned n_parts = sink ? std::max(1u, std::min(8u, n_windows / 2048u)) : 1u;
+        const unsigned n_parts = sink && !ctx->sink_device ? std::max(1u, std::min(8u, n_windows / 2048u)) : 1u;
         bool piped = sink && n_parts > 1 && ctx->h_out_bytes > 0;
         if (piped && !ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         while (piped && ctx->ev_out.size() < n_parts) {
@@ -2115,7 +2136,9 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         if (dev_err) FAIL(MGTA_ERR_INTERNAL, "device consistency flags 0x%x (stage 2, buckets [%d,%d))", dev_err, b0, b1);
         const unsigned long long bytes = *h_state;
         st->out_bytes += bytes;
-        if (sink) {
+        if (sink && ctx->sink_device) {                        // the consumer parses the records where they lie
+            if (sink(user, b0, b1, outbuf, bytes, meta_host.data()) != 0) FAIL(MGTA_ERR_ARG, "sink aborted");
+        } else if (sink) {
             if (piped && copied == bytes) {
                 CK(mgta_stream_wait(ctx->copy_stream));
             } else {
@@ -2334,6 +2357,16 @@ extern "C" int mgta_stage2(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int
     if ((rc = run_emit(ctx, sink, user, totals, st))) return rc;
     if (ctx->node_pass && ctx->tips_valid) { st->n_node_ops = 2 * ctx->n_edges; st->n_tip_items = ctx->n_tips; }
     return stage_end(ctx, st, tm);
+}
+
+extern "C" int mgta_stage2_into_sdbg(mgta_ctx *ctx, mgta_sdbg *g, int64_t *totals) {
+    if (!ctx || !g) return MGTA_ERR_ARG;
+    if (ctx->opt.world != 1) FAIL(MGTA_ERR_ARG, "stage2_into_sdbg: one shard only (the in-memory graph is one address space)");
+    ctx->sink_device = true;
+    const int rc = mgta_stage2(ctx, mgta_sdbg_sink, g, totals);
+    ctx->sink_device = false;
+    if (rc == MGTA_ERR_ARG && ctx->err == "sink aborted") ctx->err = std::string("sdbg builder: ") + mgta_sdbg_last_error(g);
+    return rc;
 }
 
 extern "C" int mgta_solid_device_buffer(mgta_ctx *ctx, void **dev_ptr, uint64_t *n_bytes) {

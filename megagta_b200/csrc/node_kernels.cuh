@@ -148,11 +148,24 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_node_count(const NodeCountPar
         const unsigned long long lo = P.off2[t], hi = P.off2[t + 1];
         if (hi == lo) continue;
         // ---- phase A: insert / accumulate (the lock-free table of k_count)
-        for (unsigned long long i = lo + tid; i < hi; i += COUNT_THREADS) {
+        constexpr int U = KW <= 2 ? 4 : (KW <= 4 ? 2 : 1);       // loads of U ops in flight before the first probe (see k_count)
+        for (unsigned long long i0 = lo + tid; i0 < hi; i0 += (unsigned long long)U * COUNT_THREADS) {
+            uint32_t keys[U][KW], pays[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned long long i = i0 + (unsigned long long)u * COUNT_THREADS;
+                const bool in = i < hi;
+#pragma unroll
+                for (int w = 0; w < KW; ++w) keys[u][w] = in ? __ldcs(P.src + (uint64_t)w * P.cap + i) : 0u;
+                pays[u] = in ? __ldcs(P.src + (uint64_t)KW * P.cap + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+            if (i0 + (unsigned long long)u * COUNT_THREADS >= hi) break;
             uint32_t key[KW];
 #pragma unroll
-            for (int w = 0; w < KW; ++w) key[w] = P.src[(uint64_t)w * P.cap + i];
-            const uint32_t pay = P.src[(uint64_t)KW * P.cap + i];
+            for (int w = 0; w < KW; ++w) key[w] = keys[u][w];
+            const uint32_t pay = pays[u];
             uint32_t ha, hb;
             edge_hash([&](int w) { return key[w]; }, KW, ha, hb);
             const uint32_t fp = (hb >> 4) + 1u;
@@ -183,6 +196,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_node_count(const NodeCountPar
                 slot = (slot + 1) & mask;
             }
             if (placed) atomicAdd((pay & 1u) ? &S.acnt[slot] : &S.cnt[slot], pay >> 1);
+            }
         }
         __syncthreads();
         const unsigned nd = s_ndist;

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels.cuh"
+#include "tma_bulk.cuh"
 
 namespace mgta {
 
@@ -108,10 +109,20 @@ __device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int
     unsigned long long g_[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) g_[j] = c_[j] ? atomicAdd(cursor + (tid * per + j), (unsigned long long)c_[j]) : 0ull;
+    // gbase[b] = (global index of the bin's first item) - (its sorted position), so that item j of the sorted order goes
+    // to gbase[b] + j (modulo 2^64).  A run that does not fit its slab is not written at all (gbase = 2^63, a value no real
+    // run can have): the cursor has counted it, the host restarts the pass with slabs that fit.
+    bool over = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int b = tid * per + j;
-        if (j < per && b < NB) { S.lbase[b] = excl + local[j]; S.gbase[b] = g_[j]; }
+        if (j < per && b < NB) {
+            const unsigned lb = excl + local[j];
+            const bool fits = !slab_cap || g_[j] + c_[j] <= (unsigned long long)b * slab_stride + slab_cap;
+            if (!fits && c_[j]) over = true;
+            S.lbase[b] = lb;
+            S.gbase[b] = fits ? g_[j] - lb : 0x8000000000000000ull;
+        }
     }
     if (tid == 0) S.lbase[NB] = total;
     __syncthreads();
@@ -120,12 +131,12 @@ __device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int
         if (b != 0xFFFFu) S.perm[S.lbase[b] + S.rank[i]] = (uint16_t)i;
     }
     __syncthreads();
-    bool over = false;
     for (unsigned j = tid; j < total; j += PART_THREADS) {
         const unsigned i = S.perm[j], b = S.bin[i];
-        const unsigned long long g = S.gbase[b] + (j - S.lbase[b]);
-        if (slab_cap && g >= (unsigned long long)b * slab_stride + slab_cap) { over = true; continue; }
-        for (int w = 0; w < IW; ++w) dst[(uint64_t)w * cap + g] = S.stage[w * P + i];
+        const unsigned long long gb = S.gbase[b];                 // may have wrapped below zero (first index < sorted position): gb + j is exact
+        if (gb == 0x8000000000000000ull) continue;
+        uint32_t *d = dst + (gb + j);
+        for (int w = 0; w < IW; ++w, d += cap) *d = S.stage[w * P + i];
     }
     if (over) atomicOr(err, (unsigned)ERR_SLAB_OVERFLOW);
     __syncthreads();
@@ -135,6 +146,8 @@ __device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int
 struct EdgePartParams {
     const uint32_t *seq;
     const uint64_t *start;
+    const uint32_t *lut;            // read lookup table (k_build_read_lut)
+    uint64_t n_lut;
     uint64_t n_reads, n_short, total_bases;
     int k;
     int filter, all_solid;          // filter: keep only solid occurrences (stage-2 counting from an is_solid vector)
@@ -167,8 +180,9 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int IW = WE + PW;
     constexpr int SW_WORDS = TP / 16 + WALK_BACK_WORDS + 12;
+    constexpr int NS = 192;                                       // start_idx entries staged per tile (reads of >= ~22-44 bases)
     __shared__ __align__(16) uint32_t sw[SW_WORDS];
-    __shared__ uint64_t s_r[2];
+    __shared__ uint64_t s_start[NS];
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, TP);
     const int tid = threadIdx.x;
@@ -182,10 +196,15 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
         for (int i = tid; i < SW_WORDS / 4; i += PART_THREADS) dstw[i] = __ldg(src + i);
     }
     for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
-    if (tid == 0) s_r[0] = find_read(P.start, 0, P.n_reads - 1, g0);
-    if (tid == 32) s_r[1] = find_read(P.start, 0, P.n_reads - 1, gend - 1);
+    // the reads of this tile: two table entries bound them, their start offsets are staged next to the read words
+    // (s_start[i] = start[r_lo + i], i <= r_hi + 1 - r_lo), so locating a position never waits on global memory
+    uint64_t r_lo, r_hi;
+    tile_read_span(P.lut, P.n_lut, g0, gend, r_lo, r_hi);
+    const bool st_smem = r_hi - r_lo + 2 <= (uint64_t)NS;          // uniform; tiles of very short reads fall back to global loads
+    if (st_smem)
+        for (int i = tid; i < (int)(r_hi - r_lo + 2); i += PART_THREADS) s_start[i] = __ldg(P.start + r_lo + i);
     __syncthreads();
-    const uint64_t r_lo = s_r[0], r_hi = s_r[1];
+    auto start_at = [&](uint64_t rr) -> uint64_t { return st_smem ? s_start[rr - r_lo] : __ldg(P.start + rr); };
     const int k = P.k;
     // Each thread ROLLS over RUN consecutive edge offsets: the (k+1)-mer E and its reverse complement R are cut out of
     // the staged words once and then advanced one base at a time (the device counterpart of the reference's
@@ -196,8 +215,13 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
     uint32_t E[WE], R[WE];
     uint64_t r = 0, s_next = 0;
     if (gt < gend) {
-        r = find_read(P.start, r_lo, r_hi, gt);
-        s_next = __ldg(P.start + r + 1);
+        uint64_t lo = r_lo, hi = r_hi;                            // largest r in [r_lo, r_hi] with start[r] <= gt
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (start_at(mid) <= gt) lo = mid; else hi = mid - 1;
+        }
+        r = lo;
+        s_next = start_at(r + 1);
         load_chars<WE>(sw, q0, k + 1, E);
         revcomp<WE>(E, k + 1, R);
     }
@@ -222,7 +246,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams
                     R[w] = (w > 0) ? __funnelshift_r(R[w], R[w > 0 ? w - 1 : 0], 2) : ((R[0] >> 2) | ((3u - c) << 30));
                 R[WE - 1] &= tail_mask;
             }
-            while (g >= s_next) { ++r; s_next = __ldg(P.start + r + 1); }
+            while (g >= s_next) { ++r; s_next = start_at(r + 1); }
             bool ok = g + (uint64_t)k + 1 <= s_next;              // the whole (k+1)-mer lies inside read r
             const bool assist = r >= P.n_short;
             if (ok && P.filter) ok = P.all_solid || assist || bit_at(P.solid, g);
@@ -390,15 +414,25 @@ struct SplitParams {
     unsigned bkt_lo, bkt_hi;
 };
 
-__global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
+// The chunk of a job arrives through the TMA engine: thread 0 takes the ticket, arms the mbarrier with the byte count and
+// issues one bulk copy per word plane (cp.async.bulk, 16-byte granules: the chunk is widened to the enclosing 4-item
+// boundaries, slots [0, a) and [a + n, ...) of the stage are never binned); the CTA waits on the barrier phase.  T4 = plane
+// stride of the stage = T + 4.
+__global__ void __launch_bounds__(PART_THREADS, 3) k_split(const SplitParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned s_job, s_b1;
+    __shared__ unsigned s_job, s_b1, s_n, s_a;
+    __shared__ __align__(8) uint64_t s_bar;
     BinSmem S;
-    const int T = (int)P.T, IW = P.IW, tid = threadIdx.x;
+    const int T = (int)P.T + 4, IW = P.IW, tid = threadIdx.x;
     bin_smem_carve(S, smem_raw, IW, T);
     const int NB = P.mode >= 2 ? (int)(P.b_hi - P.b_lo) : 1 << P.lb2;
     const unsigned n_jobs = P.chunk_pref[P.B1];
     if (*P.err & ERR_SLAB_OVERFLOW) return;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    unsigned phase = 0;
+    // bulk copies need 16-byte aligned planes (every caller carves them so); anything else takes the plain load loop
+    const bool bulk_ok = (P.cap_src & 3ull) == 0 && (reinterpret_cast<unsigned long long>(P.src) & 15ull) == 0;
     while (true) {
         if (tid == 0) {
             const unsigned j = atomicAdd(P.ticket, 1u);
@@ -410,6 +444,17 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
                     if (P.chunk_pref[mid] <= j) lo = mid; else hi = mid - 1;
                 }
                 s_b1 = lo;
+                const unsigned long long c0 = (unsigned long long)(j - P.chunk_pref[lo]) * P.T;
+                const unsigned n = (unsigned)min((unsigned long long)P.T, P.in_count[lo] - c0);
+                const unsigned long long s0 = P.in_start[lo] + c0;
+                const unsigned a = bulk_ok ? (unsigned)(s0 & 3ull) : 0u, n_ld = (n + a + 3u) & ~3u;
+                s_n = n; s_a = a;
+                if (bulk_ok) {
+                    fence_proxy_async_smem();                   // the previous job's reads of the stage (ordered by the barrier at its end)
+                    mbar_arrive_expect_tx(&s_bar, (unsigned)IW * n_ld * 4u);
+                    for (int w = 0; w < IW; ++w)
+                        bulk_g2s(S.stage + w * T, P.src + (uint64_t)w * P.cap_src + (s0 - a), n_ld * 4u, &s_bar);
+                }
             }
         }
         for (int i = tid; i < NB; i += PART_THREADS) S.cnt[i] = 0;
@@ -417,16 +462,20 @@ __global__ void __launch_bounds__(PART_THREADS) k_split(const SplitParams P) {
         const unsigned job = s_job;
         if (job >= n_jobs) break;
         const unsigned b1 = s_b1;
-        const unsigned long long c0 = (unsigned long long)(job - P.chunk_pref[b1]) * P.T;
-        const unsigned long long cnt1 = P.in_count[b1];
-        const int n = (int)min((unsigned long long)P.T, cnt1 - c0);
-        const unsigned long long s0 = P.in_start[b1] + c0;
-        for (int w = 0; w < IW; ++w) {
-            const uint32_t *s = P.src + (uint64_t)w * P.cap_src + s0;
-            for (int i = tid; i < n; i += PART_THREADS) S.stage[w * T + i] = s[i];
+        const int a = (int)s_a, n = (int)s_n + a;               // binned slots: [a, n)
+        for (int i = tid; i < a; i += PART_THREADS) S.bin[i] = 0xFFFFu;
+        if (bulk_ok) {
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+        } else {
+            const unsigned long long s0 = P.in_start[b1] + (unsigned long long)(job - P.chunk_pref[b1]) * P.T;
+            for (int w = 0; w < IW; ++w) {
+                const uint32_t *sp = P.src + (uint64_t)w * P.cap_src + s0;
+                for (int i = tid; i < n; i += PART_THREADS) S.stage[w * T + i] = sp[i];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int i = tid; i < n; i += PART_THREADS) {
+        for (int i = a + tid; i < n; i += PART_THREADS) {
             uint32_t x;
             if (P.mode == 0 || P.mode == 2) {
                 uint32_t hb;
@@ -550,14 +599,34 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
         const unsigned t = P.tile_list ? P.tile_list[s_tile] : P.t_lo + s_tile;
         const unsigned long long lo = P.off2[t], hi = P.off2[t + 1];
         if (hi == lo) continue;                                   // uniform: no divergent barrier
-        // ---- phase A: insert / count
-        for (unsigned long long i = lo + tid; i < hi; i += COUNT_THREADS) {
+        // ---- phase A: insert / count.  The loads of U items are issued back to back before the first probe: the probe loop
+        //      (volatile shared-memory reads, CAS) is a scheduling barrier for the compiler, and one dependent global load
+        //      per item left the warps waiting on HBM latency with nothing else in flight.
+        constexpr int U = WE <= 2 ? 4 : (WE <= 4 ? 2 : 1);
+        for (unsigned long long i0 = lo + tid; i0 < hi; i0 += (unsigned long long)U * COUNT_THREADS) {
+            uint32_t keys[U][WE];
+            bool assists[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned long long i = i0 + (unsigned long long)u * COUNT_THREADS;
+                assists[u] = false;
+                if (i < hi) {
+#pragma unroll
+                    for (int w = 0; w < WE; ++w) keys[u][w] = __ldcs(P.src + (uint64_t)w * P.cap + i);
+                    if (P.has_assist && P.PW) assists[u] = P.src[(uint64_t)WE * P.cap + i] == 0xFFFFFFFFu &&
+                                                           (P.PW < 2 || P.src[(uint64_t)(WE + 1) * P.cap + i] == 0xFFFFFFFFu);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < WE; ++w) keys[u][w] = 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+            if (i0 + (unsigned long long)u * COUNT_THREADS >= hi) break;
             uint32_t key[WE];
 #pragma unroll
-            for (int w = 0; w < WE; ++w) key[w] = P.src[(uint64_t)w * P.cap + i];
-            bool assist = false;
-            if (P.has_assist && P.PW) assist = P.src[(uint64_t)WE * P.cap + i] == 0xFFFFFFFFu &&
-                                                (P.PW < 2 || P.src[(uint64_t)(WE + 1) * P.cap + i] == 0xFFFFFFFFu);
+            for (int w = 0; w < WE; ++w) key[w] = keys[u][w];
+            const bool assist = assists[u];
             uint32_t ha, hb;
             edge_hash([&](int w) { return key[w]; }, WE, ha, hb);
             const uint32_t fp = (hb >> 4) + 1u;
@@ -590,6 +659,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_count(const CountParams P) {
             if (placed) {
                 atomicAdd(&S.cnt[slot], 1u);
                 if (assist) atomicAdd(&S.acnt[slot], 1u);
+            }
             }
         }
         __syncthreads();

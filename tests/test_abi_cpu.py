@@ -21,7 +21,7 @@ def declared():
 def test_library_exports_every_declared_entry_point():
     lib = ctypes.CDLL(cabi.LIB_PATH)
     names = declared()
-    assert len(names) == 23
+    assert len(names) == 33
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
 
@@ -37,3 +37,5 @@ def test_no_device_means_an_error_not_a_fallback():
     with pytest.raises(cabi.MgtaError) as e:
         cabi.Context(31, 2)
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+    with pytest.raises(cabi.MgtaError):                            # the index builder has no CPU path either
+        cabi.Sdbg(31)
