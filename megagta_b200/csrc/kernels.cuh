@@ -24,9 +24,8 @@ constexpr int SEQ_PAD_WORDS = 256;    // zero words appended to the device copy 
 constexpr int MSD_THREADS = 512;
 constexpr int CHUNK_THREADS = 512;
 constexpr int CHUNK_WARPS = CHUNK_THREADS / 32;
-constexpr int MAX_PASSES = 40;
 
-enum { MODE_HIST = 0, MODE_SCATTER = 1 };
+enum { MODE_HIST = 0 };
 enum { ERR_NEXT_LIST_FULL = 1, ERR_GIANT_LIST_FULL = 2, ERR_CHUNK_TOO_BIG = 4, ERR_OUT_OVERFLOW = 8, ERR_SORT_ORDER = 256 };
 
 struct WalkParams {
@@ -39,10 +38,6 @@ struct WalkParams {
     const uint32_t *solid;          // stage 2: one bit per base position (edge offset o of read r <=> start[r]+o)
     unsigned long long *hist;       // MODE_HIST
     unsigned long long *n_dollar;   // MODE_HIST, stage 2: number of items with a == $ (bounds the tip records)
-    unsigned long long *cursor;     // MODE_SCATTER: next free slot per bucket (batch relative)
-    uint32_t *dst;
-    uint64_t cap;
-    int b_lo, b_hi;
 };
 
 // largest r in [lo, hi] with start[r] <= g
@@ -108,18 +103,8 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const WalkParams P) {
         const uint32_t q = (uint32_t)(g - 16 * w_lo);
         auto sink = [&](const uint32_t(&key)[W], uint64_t v) {
             const int b = (int)(key[0] >> 16);
-            if (MODE == MODE_HIST) {
-                atomicAdd(P.hist + b, 1ull);
-                if (STAGE == 2 && !(key[W - 1] & 8u)) ++n_dollar;
-            } else if (b >= P.b_lo && b < P.b_hi) {
-                const uint64_t pos = atomicAdd(P.cursor + b, 1ull);
-#pragma unroll
-                for (int w = 0; w < W; ++w) P.dst[(uint64_t)w * P.cap + pos] = key[w];
-                if (STAGE == 1) {
-                    P.dst[(uint64_t)W * P.cap + pos] = (uint32_t)v;
-                    P.dst[(uint64_t)(W + 1) * P.cap + pos] = (uint32_t)(v >> 32);
-                }
-            }
+            atomicAdd(P.hist + b, 1ull);
+            if (STAGE == 2 && !(key[W - 1] & 8u)) ++n_dollar;
         };
         if (STAGE == 1) {
             if (p > L - k + 1) continue;
@@ -282,19 +267,8 @@ struct ChunkParams {
     unsigned *n_lsd;                         // windows that took the LSD passes (statistics)
     unsigned big_bin;                        // largest bin the comparison rank accepts
     int bin_bits;                            // bucket + rank sort: key bits of the counting pass (0 = LSD passes only)
-    int n_pass;
-    short pass_lsb[MAX_PASSES];
-    unsigned char pass_nb[MAX_PASSES];
     int g_full, g_rem_shift;                 // (k-1)-mer compare: full words, shift of the partial word (32 = none)
-    // stage 1
-    uint32_t *solid;
-    unsigned long long *edge_counting;
     unsigned m;
-    int need_mercy;
-    unsigned long long *mercy_out;
-    unsigned long long *mercy_count;
-    unsigned long long mercy_cap;
-    // stage 2
     int aw, ash, wpt;
     unsigned char *out;
     unsigned long long out_cap;

@@ -208,10 +208,6 @@ struct Plan {
     int stage, W, IW, k;
     unsigned CAPI, T, C;
     size_t chunk_smem;
-    std::vector<std::pair<int, int>> levels;   // (msb start bit, nbits)
-    int n_pass;
-    short pass_lsb[MAX_PASSES];
-    unsigned char pass_nb[MAX_PASSES];
     // arena carve (byte offsets)
     uint64_t cap;                              // items per batch
     size_t off_a, off_b, off_flags, off_win, off_state, off_list0, off_list1, off_giants, off_out, total;
@@ -233,25 +229,6 @@ void make_plan(Plan &pl, int stage, int k, int cap_override) {
     pl.C = capi / 2;                                               // window stride: C + largest leaf (>= one 48-item group) <= CAPI
     if (cap_override > 0) pl.T = std::max(16, std::min<int>(cap_override, (int)capi) / 2);
     pl.chunk_smem = sort_emit_smem_bytes(pl.IW, capi);
-    // MSD digit levels over the (k-1)-mer bits below the 16-bit lv1 prefix (never split a group)
-    const int GB = 2 * (k - 1);
-    pl.levels.clear();
-    for (int s = 16; s < GB;) {
-        int nb = std::min(8, GB - s);
-        pl.levels.push_back({s, nb});
-        s += nb;
-    }
-    // LSD digit passes of the on-chip sort: flag bits, skip the zero padding, then the sequence bits
-    const int TB = 32 * pl.W, FB = stage == 1 ? 6 : 4, SB = stage == 1 ? 2 * (k - 1) : 2 * k;
-    int n = 0, lsb = 0;
-    if (TB - SB > FB) {
-        pl.pass_lsb[n] = 0; pl.pass_nb[n] = (unsigned char)FB; ++n;
-        lsb = TB - SB;
-    }
-    for (; lsb < TB && n < MAX_PASSES; lsb += 8) {
-        pl.pass_lsb[n] = (short)lsb; pl.pass_nb[n] = (unsigned char)std::min(8, TB - lsb); ++n;
-    }
-    pl.n_pass = n;
 }
 
 // carve the arena for batches of up to `cap` items; returns total bytes
@@ -514,8 +491,7 @@ WalkParams walk_params(mgta_ctx *ctx) {
     memset(&P, 0, sizeof(P));
     P.seq = ctx->d_seq; P.start = ctx->d_start; P.lut = ctx->d_lut; P.n_lut = ctx->n_lut; P.n_reads = ctx->n_reads; P.n_short = ctx->n_short;
     P.total_bases = ctx->total_bases; P.k = ctx->opt.kmer_k; P.all_solid = ctx->opt.min_count == 1;
-    P.solid = ctx->d_solid; P.hist = ctx->d_hist; P.cursor = ctx->d_cursor; P.n_dollar = ctx->d_totals + 12;
-    P.b_lo = 0; P.b_hi = NUM_BUCKETS;
+    P.solid = ctx->d_solid; P.hist = ctx->d_hist; P.n_dollar = ctx->d_totals + 12;
     return P;
 }
 
@@ -581,10 +557,23 @@ void set_shard_range(mgta_ctx *ctx, uint64_t total) {
     ctx->shard_hi = shard_boundary(ctx, total, ctx->opt.rank + 1);
 }
 
+// destroys every pending phase timer (error paths, and the start of the next stage after one)
+void drop_timed(mgta_ctx *ctx) {
+    for (auto &t : ctx->timed) {
+        if (t.a) cudaEventDestroy(t.a);
+        if (t.b) cudaEventDestroy(t.b);
+    }
+    ctx->timed.clear();
+}
+
 int finish_timing(mgta_ctx *ctx, mgta_stage_stats *st) {
     for (auto &t : ctx->timed) {
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, t.a, t.b));
+        if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) {  // e.g. an event that was never recorded: nothing to report, nothing to keep
+            cudaGetLastError();
+            drop_timed(ctx);
+            FAIL(MGTA_ERR_CUDA, "phase timer could not be read");
+        }
         switch (t.phase) {
             case PH_HIST: st->ms_hist += ms; break;
             case PH_EXTRACT: st->ms_extract += ms; break;
@@ -2063,9 +2052,6 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
         CP.bin_bits = 0;
         while (CP.bin_bits < 12 && (2u << CP.bin_bits) <= pl.CAPI) ++CP.bin_bits;             // bins <= CAPI counters (the code array)
         if (const char *e = getenv("MGTA_SORT_BIN_BITS")) CP.bin_bits = std::max(0, std::min(CP.bin_bits, atoi(e)));   // A/B switch: 0 = LSD only
-        CP.n_pass = pl.n_pass;
-        memcpy(CP.pass_lsb, pl.pass_lsb, sizeof(CP.pass_lsb));
-        memcpy(CP.pass_nb, pl.pass_nb, sizeof(CP.pass_nb));
         CP.g_full = (pl.k - 1) / 16;
         CP.g_rem_shift = (pl.k - 1) % 16 ? (16 - (pl.k - 1) % 16) * 2 : 32;
         CP.m = (unsigned)ctx->opt.min_count;
@@ -2228,8 +2214,17 @@ int item_exchange_send(mgta_ctx *ctx, const unsigned *bnd, uint64_t slab_in, con
     return MGTA_OK;
 }
 
+// the two events that time a whole stage; destroyed on every exit path (an error return between stage_begin and
+// stage_end used to leak them)
 struct StageTimer {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    StageTimer() = default;
+    StageTimer(const StageTimer &) = delete;
+    StageTimer &operator=(const StageTimer &) = delete;
+    ~StageTimer() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
 };
 
 }  // namespace
@@ -2261,6 +2256,7 @@ namespace {
 int stage_begin(mgta_ctx *ctx, mgta_stage_stats *st, StageTimer &tm) {
     memset(st, 0, sizeof(*st));
     CK(cudaSetDevice(ctx->opt.device));
+    drop_timed(ctx);                                               // phase timers a failed stage left behind
     CK(cudaEventCreate(&tm.ev0));
     CK(cudaEventCreate(&tm.ev1));
     CK(cudaEventRecord(tm.ev0, ctx->stream));
@@ -2270,9 +2266,7 @@ int stage_end(mgta_ctx *ctx, mgta_stage_stats *st, StageTimer &tm) {
     CK(cudaEventRecord(tm.ev1, ctx->stream));
     CK(mgta_stream_wait(ctx->stream));                               // ev1 is the last thing on the stream
     CK(cudaEventElapsedTime(&st->ms_total, tm.ev0, tm.ev1));
-    cudaEventDestroy(tm.ev0);
-    cudaEventDestroy(tm.ev1);
-    return finish_timing(ctx, st);
+    return finish_timing(ctx, st);                                 // the StageTimer destroys its events
 }
 }  // namespace
 
