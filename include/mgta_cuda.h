@@ -254,6 +254,15 @@ int mgta_sdbg_copy(mgta_sdbg *g, int which, int c, void *host, uint64_t n_bytes)
 /* Stage 2 straight into the builder: the records of every batch are parsed where they lie in HBM (no D2H, no sink). */
 int mgta_stage2_into_sdbg(mgta_ctx *ctx, mgta_sdbg *g, int64_t *totals);
 
+/* ---- the streaming passes next to the graph build ----------------------------------------------------
+ * `megagta buildlib`: ASCII bases -> the records of <X>.bin (per read u32 length, then ceil(len / 16) u32 words, first base
+ * in bits 31..30, unused low bits zero; A C G T N a c g t n -> 0 1 2 3 2 0 1 2 3 2).  Replaces
+ * SequencePackage::AddSeqToPackedSeq_ (reference sequence_package.h:254-270, map :67-69) + SequenceManager::
+ * WriteBinarySequences (sequence_manager.cpp:375-410).  bases: host, the reads back to back; seq_off[r] .. seq_off[r + 1] =
+ * the bytes of read r; out_records: host, out_words = sum of 1 + ceil(len / 16).  FASTA/Q parsing stays with the caller. */
+int mgta_pack_reads(int device, const char *bases, const uint64_t *seq_off, uint64_t n_reads, uint32_t *out_records, uint64_t out_words);
+const char *mgta_tools_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,7 +51,7 @@ EXPORTS = ["mgta_ctx_create", "mgta_ctx_destroy", "mgta_last_error", "mgta_set_r
            "mgta_get_mercy_candidates", "mgta_get_num_mercy", "mgta_stage2", "mgta_shard_range", "mgta_get_stats", "mgta_words_per_key",
            "mgta_abi_version", "mgta_sharded_begin", "mgta_sharded_step", "mgta_sharded_result",
            "mgta_sdbg_create", "mgta_sdbg_destroy", "mgta_sdbg_last_error", "mgta_sdbg_append", "mgta_sdbg_sink", "mgta_sdbg_finish",
-           "mgta_sdbg_header", "mgta_sdbg_array", "mgta_sdbg_copy", "mgta_stage2_into_sdbg"]
+           "mgta_sdbg_header", "mgta_sdbg_array", "mgta_sdbg_copy", "mgta_stage2_into_sdbg", "mgta_pack_reads", "mgta_tools_last_error"]
 
 
 class SdbgHeader(ctypes.Structure):
@@ -117,6 +117,8 @@ def load():
                                         ctypes.POINTER(ctypes.c_uint64)]
         lib.mgta_sdbg_copy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64]
         lib.mgta_stage2_into_sdbg.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgta_pack_reads.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]
+        lib.mgta_tools_last_error.restype = ctypes.c_char_p
         _lib = lib
     return _lib
 
@@ -356,3 +358,17 @@ class Sdbg:
         out = np.zeros(n.value, dtype=np.uint8)
         self._check(self.lib.mgta_sdbg_copy(self.h, which, c, _p(out), n.value), "mgta_sdbg_copy")
         return out.view(dtype)
+
+
+def pack_reads(seqs, device=0):
+    """ASCII sequences (list of bytes) -> the <X>.bin records `megagta buildlib` writes for them (np.uint32): mgta_pack_reads"""
+    lib = load()
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, np.uint8)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    words = int(sum(1 + (len(s) + 15) // 16 for s in seqs))
+    out = np.zeros(words, dtype=np.uint32)
+    rc = lib.mgta_pack_reads(device, _p(bases) if len(bases) else None, _p(off), len(seqs), _p(out), words)
+    if rc != 0:
+        raise MgtaError("mgta_pack_reads failed (%d): %s" % (rc, lib.mgta_tools_last_error().decode()))
+    return out

@@ -55,6 +55,7 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
     const int q_off = kb + D;                                     // first key bit below the bin bits
     const int left = 2 * (k - 1) + 2 - q_off;                     // bits of `S a` below the bin bits
     const bool exact = left <= 28;
+    const bool semi = !exact && left <= 32;                       // qk holds all of `S a`: ties differ in the flag nibble only
     const int qw = q_off >> 5, qs = q_off & 31;
     unsigned short dg[8], rk[8];
     bool big = false;
@@ -129,13 +130,17 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
             unsigned pos = s;
             if (e - s > 1) {
                 const uint32_t mq = qk[i];
+                const uint32_t mf = S.keys[(W - 1) * capi + i] & 15u;
                 for (unsigned j = s; j < e; ++j) {
                     const unsigned o = S.pb[j];
                     const uint32_t oq = qk[o];
                     bool less = oq < mq;
                     if (oq == mq) {
                         less = o < i;                                              // equal keys: by item index
-                        if (!exact) {
+                        if (semi) {                                                // k = 31 with 2^19 tiles: one more word, not the key
+                            const uint32_t of = S.keys[(W - 1) * capi + o] & 15u;
+                            less = of < mf || (of == mf && less);
+                        } else if (!exact) {
 #pragma unroll
                             for (int w = W - 1; w >= 0; --w) {
                                 if (w >= tw) {

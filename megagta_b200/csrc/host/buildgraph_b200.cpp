@@ -434,8 +434,8 @@ int build_graph(int argc, char **argv) {
     int G = n_dev;                                               // all visible GPUs (CUDA_VISIBLE_DEVICES); MGTA_NUM_GPUS caps it
     if (const char *e = getenv("MGTA_NUM_GPUS")) G = std::max(1, std::min(n_dev, atoi(e)));
     G = std::min(G, 16);
-    if (opt.need_mercy && opt.min_count > 1 && G > 1) {
-        fprintf(stderr, "[B200] --need_mercy runs on one GPU: using GPU 0 only\n");
+    if (opt.need_mercy && opt.min_count > 1 && G > 1 && !opt.assist_seq_file.empty()) {
+        fprintf(stderr, "[B200] --need_mercy together with --assist_seq runs on one GPU: using GPU 0 only\n");
         G = 1;
     }
 
@@ -513,10 +513,12 @@ int build_graph(int argc, char **argv) {
     return 0;
 }
 
+int build_lib_b200(int argc, char **argv);       // buildlib_b200.cpp
+
 int main(int argc, char **argv) {
-    if (argc < 2 || strcmp(argv[1], "buildgraph") != 0) {
-        fprintf(stderr, "usage: %s buildgraph [options]   (drop-in for `megagta buildgraph`, reference src/megagta.cpp:28-60)\n", argv[0]);
-        return 1;
-    }
-    return build_graph(argc - 1, argv + 1);
+    if (argc >= 2 && strcmp(argv[1], "buildgraph") == 0) return build_graph(argc - 1, argv + 1);
+    if (argc >= 2 && strcmp(argv[1], "buildlib") == 0) return build_lib_b200(argc - 1, argv + 1);
+    fprintf(stderr, "usage: %s buildlib <read_lib_file> <out_prefix> | buildgraph [options]   (drop-ins for the `megagta` sub-programs of the same "
+                    "names, reference src/megagta.cpp:28-60)\n", argv[0]);
+    return 1;
 }

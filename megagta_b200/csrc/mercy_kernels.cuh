@@ -34,6 +34,7 @@ struct CtxPartParams {
     uint32_t *dst;
     uint64_t cap;
     unsigned *err;
+    uint32_t ha_lo, ha_last;          // only (k-1)-mers with hash in [ha_lo, ha_last] (a shard's slice of the hash space; all: 0, 2^32 - 1)
 };
 
 // One CTA = TP base positions -> <= 2 TP stage-1 items (key W words | value lo, hi), binned by the hash of S.
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_ctx_part(const CtxPartParams P
             uint32_t ha, hb;
             edge_hash([&](int w) { return w == W - 1 ? key[w] & S1_FLAG_MASK : key[w]; }, W, ha, hb);
             const unsigned b1 = ha >> P.sh1;
-            if (b1 >= P.b_lo && b1 < P.b_hi) {
+            if (b1 >= P.b_lo && b1 < P.b_hi && ha >= P.ha_lo && ha <= P.ha_last) {
                 const unsigned bin = b1 - P.b_lo;
                 const int slot = 2 * i + n_out;
                 atomicAdd(P.hist2 + ((bin << P.lb2) | ((ha >> P.sh2) & sub_mask)), 1u);

@@ -1309,7 +1309,12 @@ int launch_ctx_part_t(int W, const CtxPartParams &P, unsigned grid, cudaStream_t
     return e == cudaSuccess ? 0 : -1;
 }
 
-int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
+int mercy_apply(mgta_ctx *ctx, mgta_stage_stats *st);
+
+// sharded: only the (k-1)-mers whose hash lies in this shard's 1 / world of the 32-bit hash space are grouped (every shard
+// scans all reads; the ranges are cut in hash space, not in bins, so a shard that refines its partition still owns the
+// same keys); the candidates stay in ctx->d_cand and the caller gathers them before mercy_apply().
+int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st, bool sharded = false) {
     const int k = ctx->opt.kmer_k;
     const int W = key_words_s1(k), IW = W + 2;
     int rc = count_positions(ctx);
@@ -1340,6 +1345,8 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
     const int TP = IW <= 5 ? 2048 : 1024;
     const size_t budget = hbm_budget(ctx);
     const size_t vec_bytes = (((ctx->total_bases + 31) / 32 + 4) * 4 + 255) & ~(size_t)255;     // one position bit vector
+    const unsigned long long ha_lo = sharded ? (1ull << 32) * (unsigned)ctx->opt.rank / (unsigned)ctx->opt.world : 0ull;
+    const unsigned long long ha_hi = sharded ? (1ull << 32) * ((unsigned)ctx->opt.rank + 1) / (unsigned)ctx->opt.world : (1ull << 32);
     double slack = 1.25;
     uint64_t cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1 << 20, n_items_max / 8));
     for (int attempt = 0;; ++attempt) {
@@ -1353,10 +1360,12 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
         }
         CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));                            // candidate counter
         bool retry = false;
-        unsigned n_batches = (B1 + MAX_BINS - 1) / MAX_BINS;
+        // level-1 bins that hold hashes of [ha_lo, ha_hi) (the first and the last may be shared with a neighbour shard)
+        const unsigned R_lo = (unsigned)(ha_lo >> (32 - lb1)), R_hi = ha_hi > ha_lo ? (unsigned)((ha_hi - 1) >> (32 - lb1)) + 1 : R_lo;
+        unsigned n_batches = std::max(1u, (R_hi - R_lo + MAX_BINS - 1) / MAX_BINS);
         struct { size_t A, B, hist2, loc, off2, cur2, tot, base, in_start, chunk_pref, cur1, total; uint64_t slab_cap, capA, capB; unsigned bins, NT; } L;
         auto layout = [&](unsigned nb) {
-            L.bins = (B1 + nb - 1) / nb;
+            L.bins = std::max(1u, (R_hi - R_lo + nb - 1) / nb);
             L.NT = L.bins << lb2;
             L.slab_cap = ((uint64_t)((double)n_items_max / B1 * slack) + 2048 + 31) & ~(uint64_t)31;
             L.capA = L.slab_cap * L.bins;
@@ -1375,7 +1384,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
         if ((rc = ensure_arena(ctx, L.total + 3 * vec_bytes))) return rc;
         const size_t smem_m = mercy_smem_bytes(W, tab_cap);
         for (unsigned batch = 0; batch < n_batches && !retry; ++batch) {
-            const unsigned b_lo = batch * L.bins, b_hi = std::min(B1, b_lo + L.bins);
+            const unsigned b_lo = R_lo + batch * L.bins, b_hi = std::min(R_hi, b_lo + L.bins);
             if (b_lo >= b_hi) break;
             uint32_t *bufA = reinterpret_cast<uint32_t *>(ctx->arena + L.A), *bufB = reinterpret_cast<uint32_t *>(ctx->arena + L.B);
             uint32_t *hist2 = reinterpret_cast<uint32_t *>(ctx->arena + L.hist2);
@@ -1391,6 +1400,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
             XP0.total_bases = ctx->total_bases; XP0.k = k; XP0.sh1 = 32 - (int)lb1; XP0.sh2 = 32 - bits; XP0.lb2 = lb2;
             XP0.b_lo = b_lo; XP0.b_hi = b_hi; XP0.cursor1 = cur1; XP0.slab_cap = L.slab_cap; XP0.hist2 = hist2; XP0.dst = bufA;
             XP0.cap = L.capA; XP0.err = ctx->d_ctr + CTR_ERR;
+            XP0.ha_lo = (uint32_t)ha_lo; XP0.ha_last = (uint32_t)(ha_hi - 1);
             if ((rc = begin_timed(ctx, PH_EXTRACT))) return rc;
             const unsigned grid = (unsigned)((ctx->total_bases + TP - 1) / TP);
             if (TP == 2048 ? launch_ctx_part_t<2048>(W, XP0, grid, ctx->stream) : launch_ctx_part_t<1024>(W, XP0, grid, ctx->stream))
@@ -1461,23 +1471,32 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st) {
         const uint64_t n_cand = ctx->h_pin[0];
         if (n_cand > ctx->cand_cap) { cand_cap = n_cand + n_cand / 16 + 1024; continue; }     // counted past the end: rerun with room
         ctx->n_cand = n_cand;
-        // ---- candidates -> position bit vectors -> per-read scan (s2.cpp:106-250)
-        uint32_t *v_in = reinterpret_cast<uint32_t *>(ctx->arena + L.total), *v_out = reinterpret_cast<uint32_t *>(ctx->arena + L.total + vec_bytes),
-                 *v_any = reinterpret_cast<uint32_t *>(ctx->arena + L.total + 2 * vec_bytes);
-        CK(cudaMemsetAsync(v_in, 0, 3 * vec_bytes, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));
-        if (n_cand) {
-            k_mercy_bits<<<(unsigned)((n_cand + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cand, n_cand, v_in, v_out, v_any);
-            k_mercy_reads<<<(unsigned)((ctx->n_short + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_short, k, v_in, v_out, v_any,
-                                                                                        ctx->d_solid, ctx->d_totals + 11);
-            CK(cudaGetLastError());
-            st->n_launches += 2;
-        }
-        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(mgta_stream_wait(ctx->stream));
-        ctx->num_mercy = ctx->h_pin[0];
         break;
     }
+    if (sharded) return MGTA_OK;                                   // the caller gathers the candidates of all shards first
+    return mercy_apply(ctx, st);
+}
+
+// ---- candidates (ctx->d_cand, ctx->n_cand) -> position bit vectors -> per-read scan extending is_solid (s2.cpp:106-250).
+// The candidate buffers of the partition are dead by now: the three vectors take the start of the arena.
+int mercy_apply(mgta_ctx *ctx, mgta_stage_stats *st) {
+    int rc;
+    const size_t vec_bytes = (((ctx->total_bases + 31) / 32 + 4) * 4 + 255) & ~(size_t)255;     // one position bit vector
+    if ((rc = ensure_arena(ctx, 3 * vec_bytes))) return rc;
+    uint32_t *v_in = reinterpret_cast<uint32_t *>(ctx->arena), *v_out = reinterpret_cast<uint32_t *>(ctx->arena + vec_bytes),
+             *v_any = reinterpret_cast<uint32_t *>(ctx->arena + 2 * vec_bytes);
+    CK(cudaMemsetAsync(v_in, 0, 3 * vec_bytes, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_totals + 11, 0, 8, ctx->stream));
+    if (ctx->n_cand) {
+        k_mercy_bits<<<(unsigned)((ctx->n_cand + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cand, ctx->n_cand, v_in, v_out, v_any);
+        k_mercy_reads<<<(unsigned)((ctx->n_short + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_start, ctx->n_short, ctx->opt.kmer_k, v_in, v_out, v_any,
+                                                                                    ctx->d_solid, ctx->d_totals + 11);
+        CK(cudaGetLastError());
+        st->n_launches += 2;
+    }
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_totals + 11, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(mgta_stream_wait(ctx->stream));
+    ctx->num_mercy = ctx->h_pin[0];
     ctx->mercy_valid = true;
     return MGTA_OK;
 }

@@ -28,7 +28,11 @@ static int sdbg_dump(int argc, char **argv) {
     if (argc < 4) { fprintf(stderr, "usage: sdbgdump <prefix> <need_mult> <out>\n"); return 1; }
     const bool need_mul = atoi(argv[2]) != 0;
     SuccinctDBG g;
+    struct timeval t0, t1;
+    gettimeofday(&t0, NULL);
     g.LoadFromMultiFile(argv[1], need_mul);
+    gettimeofday(&t1, NULL);
+    fprintf(stderr, "load_seconds %.6f\n", (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_usec - t0.tv_usec));
     FILE *f = fopen(argv[3], "wb");
     if (!f) return 1;
     char nm[64];

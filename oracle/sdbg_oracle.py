@@ -27,8 +27,12 @@ def read_dump(path):
 
 
 def ref_dump(ref_bin, prefix, need_mult, out):
-    subprocess.run([ref_bin, "sdbgdump", prefix, "1" if need_mult else "0", out], check=True, capture_output=True)
-    return read_dump(out)
+    r = subprocess.run([ref_bin, "sdbgdump", prefix, "1" if need_mult else "0", out], check=True, capture_output=True, text=True)
+    d = read_dump(out)
+    for line in r.stderr.splitlines():
+        if line.startswith("load_seconds"):
+            d["_load_seconds"] = line.split()[1].encode()       # wall time of SuccinctDBG::LoadFromMultiFile alone (not a section)
+    return d
 
 
 def _pack_bits(bits):

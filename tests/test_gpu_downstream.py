@@ -31,7 +31,9 @@ def contigs(path):
 
 
 def denovo(prefix, min_contig):
-    r = subprocess.run([O.REF_BIN, "denovo", "-s", prefix, "-o", prefix, "-t", "4", "--min_standalone", "400", "--max_tip_len", "150",
+    # one thread: with -t 4 the reference's own bubble / tip removal is not deterministic (5 different contig sets in 8 runs
+    # on its own meta200k files: equal-support alleles are resolved in thread-arrival order)
+    r = subprocess.run([O.REF_BIN, "denovo", "-s", prefix, "-o", prefix, "-t", "1", "--min_standalone", "400", "--max_tip_len", "150",
                         "--min_contig", str(min_contig)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     return contigs(prefix + ".contigs.fa"), r.stderr

@@ -153,3 +153,38 @@ def test_one_shard_through_the_sharded_entry_points(read_lib):
         ec = ctx.sharded(1, lambda c: pytest.fail("no collective expected"))
         stream, meta, totals = ctx.sharded(2, lambda c: pytest.fail("no collective expected"))
     assert np.array_equal(ec, whole[0]) and stream == whole[1] and np.array_equal(meta, whole[2])
+
+
+@pytest.mark.parametrize("ds,k,m", [("smoke", 31, 2), ("adversarial", 27, 3), ("xander", 29, 2), ("meta200k", 31, 2)])
+def test_sharded_mercy(read_lib, golden, ds, k, m):
+    """--need_mercy on several shards: is_solid summed over the shards, candidates of every shard's slice of the (k-1)-mer
+    hash space all-gathered, per-read scan on every shard.  Same candidates, "Number mercy", is_solid and graph as one shard
+    (which the mercy goldens of the unmodified reference pin, tests/test_gpu_parity.py)."""
+    _, rd = read_lib(ds)
+    with cabi.Context(k, m, need_mercy=True) as ctx:
+        ctx.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+        ec0 = ctx.stage1()
+        cand0, nm0, solid0 = np.sort(ctx.mercy_candidates()), ctx.num_mercy(), ctx.get_is_solid()
+        stream0, meta0, totals0 = ctx.stage2()
+    g = golden["cases"].get("%s_k%d_m%d_mercy" % (ds, k, m))
+    if g:
+        assert nm0 == g["num_mercy"] and len(cand0) == g["mercy_cand_n"] and O.stream_hash(stream0) == g["stream_hash"]
+    for world in (2, 3):
+        ctxs = [cabi.Context(k, m, need_mercy=True, rank=r, world=world) for r in range(world)]
+        try:
+            for c in ctxs:
+                c.set_reads(rd["seq"], rd["start"], max_len=rd["max_len"])
+            ecs, n1 = lockstep(ctxs, 1)
+            assert n1 >= 4                                     # item exchange, edge_counting, is_solid, candidate counts (+ candidates)
+            for c, ec in zip(ctxs, ecs):
+                assert np.array_equal(ec, ec0)
+                assert c.num_mercy() == nm0
+                assert np.array_equal(np.sort(c.mercy_candidates()), cand0)
+                assert np.array_equal(c.get_is_solid(), solid0)
+            res, _ = lockstep(ctxs, 2)
+            assert b"".join(r[0] for r in res) == stream0
+            assert np.array_equal(sum(r[1] for r in res), meta0)
+            assert np.array_equal(sum(r[2] for r in res), totals0)
+        finally:
+            for c in ctxs:
+                c.close()
