@@ -262,6 +262,15 @@ int mgta_stage2_into_sdbg(mgta_ctx *ctx, mgta_sdbg *g, int64_t *totals);
  * the bytes of read r; out_records: host, out_words = sum of 1 + ceil(len / 16).  FASTA/Q parsing stays with the caller. */
 int mgta_pack_reads(int device, const char *bases, const uint64_t *seq_off, uint64_t n_reads, uint32_t *out_records, uint64_t out_words);
 const char *mgta_tools_last_error(void);
+/* `megagta findstart` (reference fast_kmer_filter.cpp:49-218): every read of a batch of .bin records (n_reads records in
+ * n_words u32) of at least min_len bases is translated on both strands in all three frames (standard code, sequence/
+ * Codon.C:8-90) and every window of aa_k residues is looked up among the model k-mers.  model_kmers: [n_model][2] u64, 5 bits
+ * per residue in the codes of ProtKmer::setUp (prot_kmer.h:26-43: ARNDCQEGHI = 0..9, LKMFPSTWYV = 10..19, * = 20), residues
+ * 0..11 in word 0 (first residue most significant), 12..23 in word 1; of equal k-mers the first counts (HashSetST::insert).
+ * A hit: hit_pos = read << 24 | strand << 23 | nucleotide offset in the strand's own direction, hit_model = index of the
+ * model k-mer.  *n_hits keeps counting past hits_cap (call again with room). */
+int mgta_find_seeds(int device, const uint64_t *model_kmers, uint64_t n_model, int aa_k, const uint32_t *records, uint64_t n_words,
+                    uint64_t n_reads, int min_len, uint64_t *hit_pos, uint32_t *hit_model, uint64_t hits_cap, uint64_t *n_hits);
 
 #ifdef __cplusplus
 }

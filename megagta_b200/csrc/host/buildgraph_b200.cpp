@@ -514,11 +514,14 @@ int build_graph(int argc, char **argv) {
 }
 
 int build_lib_b200(int argc, char **argv);       // buildlib_b200.cpp
+int find_start_b200(int argc, char **argv);      // findstart_b200.cpp
 
 int main(int argc, char **argv) {
     if (argc >= 2 && strcmp(argv[1], "buildgraph") == 0) return build_graph(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "buildlib") == 0) return build_lib_b200(argc - 1, argv + 1);
-    fprintf(stderr, "usage: %s buildlib <read_lib_file> <out_prefix> | buildgraph [options]   (drop-ins for the `megagta` sub-programs of the same "
+    if (argc >= 2 && strcmp(argv[1], "findstart") == 0) return find_start_b200(argc - 1, argv + 1);
+    fprintf(stderr, "usage: %s buildlib <read_lib_file> <out_prefix> | buildgraph [options] | findstart <ref_seq> <reads.bin> <k_size> [threads] [contigs]\n"
+                    "       (drop-ins for the `megagta` sub-programs of the same "
                     "names, reference src/megagta.cpp:28-60)\n", argv[0]);
     return 1;
 }
