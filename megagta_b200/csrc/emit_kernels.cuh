@@ -38,8 +38,14 @@ __device__ __forceinline__ int key_cmp(const uint32_t *keys, unsigned capi, unsi
 // Returns false (uniformly, nothing written to S.pa) when a bin holds more than P.big_bin items: low-complexity windows
 // take the LSD path below.
 
+// The bin bits are taken from (key word 0 - base0) << kb, base0 = the prefix of the window's first tile and kb = the leading
+// zeros of the window's span in that word: a window of a few consecutive prefix tiles then spreads over at least half of
+// the bins wherever it lies.  (Taking the bits below the prefix the window SHARES wasted bins whenever the window crossed
+// an aligned boundary -- 2^j-fold with probability 2^-j, so every level cost the same: simulated mean bin occupancy 9.5
+// instead of 2.2, and every window past 64 per bin fell to the LSD passes.)  Subtracting a constant from the first word
+// keeps the key order, so everything below works on K' = (word 0 - base0, word 1, ...).
 template <int W>
-__device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, unsigned capi, unsigned n, int kb, int D,
+__device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, unsigned capi, unsigned n, int kb, uint32_t base0, int D,
                                                  unsigned *s_big, unsigned big_bin, int k) {
     // bin counters: u16 pairs packed in the (otherwise idle) per-warp LSD counter array -- 32-bit shared atomics on the
     // half that belongs to the bin return the arrival rank; <= 4096 items per window, so a half never carries over.
@@ -63,12 +69,13 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
     for (int r = 0; r < 8; ++r) {
         const unsigned i = tid + r * CHUNK_THREADS;
         if (i < n) {
-            const unsigned d = (S.keys[i] << kb) >> (32 - D);
+            const uint32_t w0 = S.keys[i] - base0;
+            const unsigned d = (w0 << kb) >> (32 - D);
             const unsigned sh = (d & 1u) * 16u;
             const unsigned a = (atomicAdd(&hist[d >> 1], 1u << sh) >> sh) & 0xFFFFu;
             dg[r] = (unsigned short)d; rk[r] = (unsigned short)a;
             big = big || a >= big_bin;
-            const uint32_t k0 = qw < W ? S.keys[qw * capi + i] : 0u;
+            const uint32_t k0 = qw == 0 ? w0 : (qw < W ? S.keys[qw * capi + i] : 0u);
             const uint32_t k1 = qw + 1 < W ? S.keys[(qw + 1) * capi + i] : 0u;
             uint32_t q = __funnelshift_l(k1, k0, qs);             // 32 key bits from bit q_off on
             if (exact) q = left > 0 ? (((q >> (32 - left)) << 4) | (S.keys[(W - 1) * capi + i] & 15u)) : (S.keys[(W - 1) * capi + i] & 15u);
@@ -133,6 +140,7 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
                 const uint32_t mf = S.keys[(W - 1) * capi + i] & 15u;
                 for (unsigned j = s; j < e; ++j) {
                     const unsigned o = S.pb[j];
+                    if (o == i) continue;                                          // itself: it would take the whole tie-break below
                     const uint32_t oq = qk[o];
                     bool less = oq < mq;
                     if (oq == mq) {
@@ -150,7 +158,7 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
                             }
                         }
                     }
-                    pos += (o != i && less) ? 1u : 0u;
+                    pos += less ? 1u : 0u;
                 }
             }
             S.pa[pos] = (uint16_t)i;
@@ -200,8 +208,16 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
             n = 0;
         }
         // key bits all items of the window share: the tiles of a window are in prefix order, so first ^ last bounds them
-        int kb = P.depth_min;
-        if (n > 1) kb = min(kb, __clz(P.src[lo] ^ P.src[lo + n - 1]));
+        // (the LSD passes stop there); the bucket + rank sort takes its bins from the window's SPAN instead (see above)
+        int kb = P.depth_min, kspan = P.depth_min;
+        uint32_t base0 = 0;
+        if (n > 1) {
+            const uint32_t f0 = P.src[lo], l0 = P.src[lo + n - 1];
+            const uint32_t low = kb >= 32 ? 0u : (0xFFFFFFFFu >> kb);             // bits below the tile prefix
+            base0 = f0 & ~low;
+            kspan = min(kspan, __clz(((l0 | low) - base0) | 1u));
+            kb = min(kb, __clz(f0 ^ l0));
+        }
         // ---- load the window (coalesced per word array)
         for (unsigned i = tid; i < n; i += CHUNK_THREADS) {
 #pragma unroll
@@ -213,7 +229,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParam
         //      then the S bits [kb, 2(k-1)) from the least significant byte up.  One __match_any_sync per item and pass;
         //      digit, warp-local rank and item stay in registers between the counting and the scatter half.
         bool sorted = n <= 1;
-        if (!sorted && P.bin_bits > 0) sorted = bucket_rank_sort<W>(S, fld, capi, n, kb, P.bin_bits, &s_big, P.big_bin, P.k);
+        if (!sorted && P.bin_bits > 0) sorted = bucket_rank_sort<W>(S, fld, capi, n, kspan, base0, P.bin_bits, &s_big, P.big_bin, P.k);
         if (!sorted) {
             if (tid == 0 && P.n_lsd) atomicAdd(P.n_lsd, 1u);
             const unsigned slice = (((n + CHUNK_WARPS - 1) / CHUNK_WARPS) + 31) & ~31u;

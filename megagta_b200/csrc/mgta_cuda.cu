@@ -738,9 +738,9 @@ int launch_item_part(int WE, bool plus, bool real_only, const ItemPartParams &P,
 
 int launch_node_part(int KW, bool eplus, const NodePartParams &P, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
-    const unsigned grid = (unsigned)((P.n_edges + NODE_EDGES - 1) / NODE_EDGES);
     KW_SWITCH(KW, {
-        const size_t smem = bin_smem_bytes(KK + 1, NODE_EDGES * 2);
+        const unsigned grid = (unsigned)((P.n_edges + node_edges(KK) - 1) / node_edges(KK));
+        const size_t smem = bin_smem_bytes(KK + 1, node_edges(KK) * 2);
         if (eplus) {
             e = cudaFuncSetAttribute(k_node_part<KK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) k_node_part<KK, true><<<grid, PART_THREADS, smem, st>>>(P);

@@ -39,12 +39,15 @@ struct NodePartParams {
     unsigned long long slab_stride;
 };
 
-constexpr int NODE_EDGES = 1024;      // edges per CTA -> 2048 op slots
+// edges per CTA (2 op slots each): with up to 1024 bins per CTA a small tile leaves runs of two ops per bin (one cursor atomic
+// and one partial sector per op); 2048 edges while the staged ops fit two CTAs per SM
+__host__ __device__ constexpr int node_edges(int KW) { return KW + 1 <= 4 ? 2048 : 1024; }
 
 // KW = kmer_words(k); EPLUS: the edge has one word more than the k-mer (k % 16 == 0)
 template <int KW, bool EPLUS>
 __global__ void __launch_bounds__(PART_THREADS) k_node_part(const NodePartParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NODE_EDGES = node_edges(KW);
     constexpr int WE = KW + (EPLUS ? 1 : 0), IW = KW + 1, SLOTS = NODE_EDGES * 2;
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, SLOTS);
