@@ -703,10 +703,11 @@ int launch_count(int WE, bool plus, const CountParams &P, unsigned grid, size_t 
 template <int PER>
 int launch_item_part_t(int WE, bool plus, const ItemPartParams &P, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
-    const unsigned per_cta = ITEM_SLOTS / PER;
-    const unsigned grid = (unsigned)((P.n_edges + per_cta - 1) / per_cta);
     WE_SWITCH(WE, {
-        const size_t smem = bin_smem_bytes(EE + (plus ? 1 : 0) + 1, ITEM_SLOTS);
+        const int iw = EE + (plus ? 1 : 0) + 1;
+        const unsigned per_cta = item_slots(iw, PER) / PER;
+        const unsigned grid = (unsigned)((P.n_edges + per_cta - 1) / per_cta);
+        const size_t smem = bin_smem_bytes(iw, item_slots(iw, PER));
         if (plus) {
             e = cudaFuncSetAttribute(k_item_part<EE, true, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) k_item_part<EE, true, PER><<<grid, PART_THREADS, smem, st>>>(P);

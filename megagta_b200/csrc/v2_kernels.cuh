@@ -804,7 +804,9 @@ struct ItemPartParams {
     unsigned long long slab_cap, slab_stride;
 };
 
-constexpr int ITEM_SLOTS = 3072;      // item slots per CTA: 512 edges x 6 items, or 1536 edges x 2 real items
+// item slots per CTA: 512 edges x 6 items; 2048 edges x 2 real items while the staged items leave two CTAs per SM (IW <= 4),
+// else 1536 x 2
+__host__ __device__ constexpr int item_slots(int IW, int PER) { return PER == 2 && IW <= 4 ? 4096 : 3072; }
 
 // PER = 6: all stage-2 items of an edge ($-items unconditionally; the group logic drops the covered ones);
 // PER = 2: the real items only -- the $-items of the tip k-mers come from the node pass (k_row_part)
@@ -812,7 +814,7 @@ template <int WE, bool PLUS, int PER>
 __global__ void __launch_bounds__(PART_THREADS) k_item_part(const ItemPartParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W2 = PLUS ? WE + 1 : WE;
-    constexpr int IW = W2 + 1, SLOTS = ITEM_SLOTS, EDGES = ITEM_SLOTS / PER;
+    constexpr int IW = W2 + 1, SLOTS = item_slots(IW, PER), EDGES = SLOTS / PER;
     BinSmem S;
     bin_smem_carve(S, smem_raw, IW, SLOTS);
     const int tid = threadIdx.x;
