@@ -168,11 +168,14 @@ __device__ __forceinline__ bool bucket_rank_sort(ChunkSmem &S, uint32_t *qk, uns
     return true;
 }
 
-template <int W>
+// CAPI_T: the window capacity as a compile-time constant (0 = P.CAPI at run time).  Every access to the staged keys is
+// keys[w * capi + idx]: with a constant plane stride the multiplications become immediate offsets (they were 17 % of the
+// kernel's instructions, attributed to the lines that define `capi` and `S.keys`).
+template <int W, int CAPI_T>
 __global__ void __launch_bounds__(CHUNK_THREADS, 2) k_sort_emit(const ChunkParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int IW = W + 1;
-    const unsigned capi = P.CAPI, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt = (1u << lane) - 1;
+    const unsigned capi = CAPI_T ? (unsigned)CAPI_T : P.CAPI, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lt = (1u << lane) - 1;
     ChunkSmem S;
     uint32_t *fld;
     {

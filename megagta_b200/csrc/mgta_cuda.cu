@@ -199,6 +199,14 @@ namespace {
         default: break;                                            \
     }
 
+#define W_SWITCH3(W, ...)                                          \
+    switch (W) {                                                   \
+        case 1: { constexpr int WW = 1; __VA_ARGS__; } break;      \
+        case 2: { constexpr int WW = 2; __VA_ARGS__; } break;      \
+        case 3: { constexpr int WW = 3; __VA_ARGS__; } break;      \
+        default: break;                                            \
+    }
+
 template <int STAGE, int MODE>
 void launch_walk(int W, const WalkParams &P, unsigned grid, cudaStream_t st) {
     W_SWITCH(W, (k_walk<WW, STAGE, MODE><<<grid, WALK_THREADS, 0, st>>>(P)));
@@ -1900,12 +1908,20 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
     const unsigned T = split_chunk_items(IW);
 
     int occ = 1;
+    const bool capi_const = pl.CAPI == 4096 && W <= 3;             // the usual shape (k <= 45) gets the constant-stride instantiation
     {
         cudaError_t e = cudaSuccess;
-        W_SWITCH(W, {
-            e = cudaFuncSetAttribute(k_sort_emit<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sort_emit<WW>, CHUNK_THREADS, pl.chunk_smem);
-        });
+        if (capi_const) {
+            W_SWITCH3(W, {
+                e = cudaFuncSetAttribute(k_sort_emit<WW, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sort_emit<WW, 4096>, CHUNK_THREADS, pl.chunk_smem);
+            });
+        } else {
+            W_SWITCH(W, {
+                e = cudaFuncSetAttribute(k_sort_emit<WW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.chunk_smem);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sort_emit<WW, 0>, CHUNK_THREADS, pl.chunk_smem);
+            });
+        }
         if (e != cudaSuccess) FAIL(MGTA_ERR_CUDA, "k_sort_emit setup failed: %s", cudaGetErrorString(e));
     }
     occ = std::max(1, occ);
@@ -2113,7 +2129,8 @@ int run_emit(mgta_ctx *ctx, mgta_bucket_sink sink, void *user, int64_t *totals, 
             const unsigned cnt = CP.win_hi - CP.win_lo;
             if (c) CK(cudaMemsetAsync(ctx->d_ctr + CTR_TICKET, 0, 4, ctx->stream));
             const unsigned cgrid = std::max(1u, std::min<unsigned>(cnt, (unsigned)(ctx->sm_count * occ)));
-            W_SWITCH(W, (k_sort_emit<WW><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP)));
+            if (capi_const) { W_SWITCH3(W, (k_sort_emit<WW, 4096><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP))); }
+            else { W_SWITCH(W, (k_sort_emit<WW, 0><<<cgrid, CHUNK_THREADS, pl.chunk_smem, ctx->stream>>>(CP))); }
             // windows took their space in completion order: scan the byte counts and copy every window to its place in bucket order
             k_out_scan<<<1, 1024, 0, ctx->stream>>>(state, CP.win_lo, CP.win_hi, ctx->d_totals + 15, d_end + c);
             k_out_gather<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(state, CP.win_lo, CP.win_hi, tmpbuf, outbuf);
