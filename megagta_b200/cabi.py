@@ -335,6 +335,27 @@ class Sdbg:
         buf = np.frombuffer(stream_bytes, dtype=np.uint8) if len(stream_bytes) else np.zeros(0, np.uint8)
         self._check(self.lib.mgta_sdbg_append(self.h, b0, b1, _p(buf) if len(buf) else None, len(buf), _p(meta)), "mgta_sdbg_append")
 
+    def from_files(self, prefix, delivery_bytes=1 << 29):
+        """the graph files <prefix>.sdbg_info / .sdbg.<i> (what SuccinctDBG::LoadFromMultiFile reads, succinct_dbg.cpp:595-723):
+        the bucket ranges of the files are put back into bucket order (the reference's writer threads scatter them) and
+        handed over in deliveries of about delivery_bytes"""
+        from . import sdbg_io
+        hdr, rows = sdbg_io.read_info(prefix)
+        wpt = hdr["words_per_tip_label"]
+        files = [np.memmap("%s.sdbg.%d" % (prefix, i), dtype=np.uint8, mode="r") if os.path.getsize("%s.sdbg.%d" % (prefix, i)) else
+                 np.zeros(0, np.uint8) for i in range(hdr["num_threads"])]
+        nb = hdr["num_buckets"]
+        size = rows[:, 3] * 2 + rows[:, 5] * 2 + rows[:, 4] * 4 * wpt
+        b0, parts, acc = 0, [], 0
+        for b in range(nb):
+            if rows[b, 1] != -1:
+                parts.append(files[int(rows[b, 1])][int(rows[b, 2]):int(rows[b, 2]) + int(size[b])])
+                acc += int(size[b])
+            if acc >= delivery_bytes or b == nb - 1:
+                self.append(b0, b + 1, np.concatenate(parts).tobytes() if parts else b"", rows[b0:b + 1, 3:6])
+                b0, parts, acc = b + 1, [], 0
+        return hdr
+
     def from_stage2(self, ctx):
         """stage 2 of `ctx` straight into the builder (records parsed in HBM) -> totals int64[10]"""
         totals = np.zeros(10, dtype=np.int64)

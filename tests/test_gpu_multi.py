@@ -55,3 +55,27 @@ def test_cpp_driver_on_two_gpus_writes_one_file_per_gpu(golden, read_lib, tmp_pa
         assert set(rows[rows[:, 3] > 0][:, 1].tolist()) == {0, 1}            # both files hold buckets
         assert hdr["total_size"] == g["total_size"] and hdr["num_tips"] == g["num_tips"]
         assert O.stream_hash(stream) == g["stream_hash"] and O.meta_hash(meta) == g["meta_hash"]
+
+
+def test_cpp_driver_with_mercy_on_two_gpus(golden, read_lib, tmp_path):
+    """--need_mercy with MGTA_NUM_GPUS=2 (real NCCL: is_solid all-reduce, candidate all-gathers): the graph and "Number mercy"
+    of the unmodified reference run with --need_mercy"""
+    import re
+    import torch
+    from megagta_b200 import sdbg_io
+    from oracle import oracle as O
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    binary = os.path.join(ROOT, "megagta_b200", "bin", "megagta_b200")
+    for case in ("smoke_k31_m2_mercy", "adversarial_k27_m3_mercy"):
+        g = golden["cases"][case]
+        prefix, _ = read_lib(g["dataset"])
+        out = str(tmp_path / case)
+        r = subprocess.run([binary, "buildgraph", "-k", str(g["k"]), "-m", str(g["m"]), "--host_mem", "4e9", "--num_cpu_threads", "4",
+                            "--num_output_threads", "1", "--read_lib_file", prefix, "--output_prefix", out, "--need_mercy"],
+                           capture_output=True, text=True, timeout=600, env=dict(os.environ, MGTA_NUM_GPUS="2"))
+        assert r.returncode == 0, r.stderr[-3000:]
+        hdr, stream, meta = sdbg_io.canonical(out)
+        assert hdr["num_threads"] == 2
+        assert int(re.search(r"Number mercy: (\d+)", r.stderr).group(1)) == g["num_mercy"]
+        assert O.stream_hash(stream) == g["stream_hash"] and O.meta_hash(meta) == g["meta_hash"]

@@ -117,3 +117,35 @@ def test_gpu_index_of_our_files_equals_the_reference_loader(read_lib, tmp_path):
         assert set(got) == set(ref)
         bad = [s for s in ref if got[s] != ref[s]]
         assert not bad, bad
+        with cabi.Sdbg(k, bool(need_mult)) as g:                 # and straight from the files, like LoadFromMultiFile
+            g.from_files(ours)
+            g.finish()
+            got = device_sections(g, cabi, need_mult)
+        bad = [s for s in ref if got[s] != ref[s]]
+        assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_gpu_index_from_the_files_of_two_gpus(read_lib, tmp_path):
+    """one .sdbg.<g> per GPU (MGTA_NUM_GPUS=2): the loader walks the sdbg_info rows across both files"""
+    import torch
+    from megagta_b200 import cabi
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    if not O.have_ref() or "sdbgdump" not in open(O.REF_BIN, "rb").read().decode("latin1"):
+        pytest.skip("oracle/_ref/megagta_ref with sdbgdump not built")
+    prefix, _ = read_lib("meta200k")
+    ours = str(tmp_path / "ours")
+    binp = os.path.join(os.path.dirname(cabi.LIB_PATH), "..", "bin", "megagta_b200")
+    r = subprocess.run([binp, "buildgraph", "-k", "31", "-m", "2", "--host_mem", "4e9", "--num_cpu_threads", "4", "--num_output_threads", "1",
+                        "--read_lib_file", prefix, "--output_prefix", ours], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, MGTA_NUM_GPUS="2"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = SO.ref_dump(O.REF_BIN, ours, 1, str(tmp_path / "dump"))
+    ref.pop("_load_seconds", None)
+    with cabi.Sdbg(31, True) as g:
+        assert g.from_files(ours)["num_threads"] == 2
+        g.finish()
+        got = device_sections(g, cabi, 1)
+    bad = [s for s in ref if got[s] != ref[s]]
+    assert not bad, bad
