@@ -989,9 +989,16 @@ int count_batch_tail(mgta_ctx *ctx, const CountPlan &cp, const CountLay &L, unsi
     if (ne) {
         const size_t row = (size_t)(WE + 1) * 4;
         if (ctx->n_edges + ne > ctx->edges_cap) {
-            const uint64_t ncap = std::max<uint64_t>(ctx->n_edges + ne, n_batches > 1 ? (ctx->n_edges + ne) * (n_batches - batch) / 1 : 0);
+            // room for the batches still to come, extrapolated from the share counted so far (hash batches are balanced);
+            // if that much is not available, exactly what is needed now
+            const uint64_t need = ctx->n_edges + ne;
+            uint64_t ncap = n_batches > 1 ? std::max<uint64_t>(need, (uint64_t)((double)need * n_batches / (batch + 1) * 1.08)) : need;
             uint32_t *nbuf = nullptr;
-            CK(cudaMalloc(&nbuf, ncap * row));
+            if (ncap > need && cudaMalloc(&nbuf, ncap * row) != cudaSuccess) {
+                cudaGetLastError();
+                nbuf = nullptr; ncap = need;
+            }
+            if (!nbuf) CK(cudaMalloc(&nbuf, ncap * row));
             if (ctx->n_edges) CK(cudaMemcpyAsync(nbuf, ctx->d_edges, ctx->n_edges * row, cudaMemcpyDeviceToDevice, ctx->stream));
             CK(mgta_stream_wait(ctx->stream));
             cudaFree(ctx->d_edges);
