@@ -839,7 +839,9 @@ int make_count_plan(mgta_ctx *ctx, CountMode mode, CountPlan &cp) {
     // overflow pass).  Keeping the mean high matters: one more bit doubles the level-1 bins, and past MAX_BINS the reads
     // are scanned once per batch of bins.
     int bits = 2;
-    while (bits < 28 && (cp.n_pos >> bits) > (uint64_t)cp.tab_cap * 3 / 4) ++bits;
+    unsigned fill_pct = 75;
+    if (const char *e = getenv("MGTA_TILE_FILL_PCT")) fill_pct = (unsigned)std::max(10, std::min(400, atoi(e)));   // A/B switch
+    while (bits < 28 && (cp.n_pos >> bits) > (uint64_t)cp.tab_cap * fill_pct / 100) ++bits;
     cp.bits = bits;
     cp.lb2 = (unsigned)std::min(10, bits / 2);
     cp.lb1 = (unsigned)bits - cp.lb2;
