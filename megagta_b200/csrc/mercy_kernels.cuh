@@ -107,8 +107,20 @@ struct MercyParams {
     unsigned *err;
 };
 
-__host__ __device__ inline size_t mercy_smem_bytes(int W, unsigned cap) {
-    return (size_t)cap * (4 + 4 * (size_t)W + 48 + 2 + 2);
+// compact: the three 4x4 count tables as saturating 2-bit fields (one u32 each) -- enough for min_count <= 3, and a third
+// of the shared memory per (k-1)-mer, so three CTAs share an SM instead of one
+__host__ __device__ inline size_t mercy_smem_bytes(int W, unsigned cap, bool compact = false) {
+    return (size_t)cap * (4 + 4 * (size_t)W + (compact ? 12 : 48) + 2 + 2);
+}
+
+// saturating increment of the 2-bit field `x` (0..15) of *w
+__device__ __forceinline__ void sat_inc2(uint32_t *w, int x) {
+    uint32_t old = *(volatile uint32_t *)w;
+    while (((old >> (2 * x)) & 3u) != 3u) {
+        const uint32_t prev = atomicCAS(w, old, old + (1u << (2 * x)));
+        if (prev == old) return;
+        old = prev;
+    }
 }
 
 // saturating increment of byte `b` of *w (counts only matter up to min_count <= 255)
@@ -121,21 +133,27 @@ __device__ __forceinline__ void sat_inc(uint32_t *w, int b) {
     }
 }
 
-template <int W>
+// COMPACT: tables of 2-bit saturating fields, TW = 3 words per slot (cph | ctn | cht, field index hi * 4 + lo); else bytes, 12 words
+template <int W, bool COMPACT>
 __global__ void __launch_bounds__(COUNT_THREADS) k_mercy(const MercyParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TW = COMPACT ? 3 : 12;
     const unsigned cap = P.tab_cap, mask = cap - 1, tid = threadIdx.x, lane = tid & 31;
     uint32_t *tag = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *keys = tag + cap;                                   // [W][cap]
-    uint32_t *tabs = keys + (size_t)W * cap;                      // [cap][12]: cph 16 B | ctn 16 B | cht 16 B, byte index hi * 4 + lo
-    uint16_t *gmask = reinterpret_cast<uint16_t *>(tabs + (size_t)12 * cap);   // has_in | has_out << 4 | l_has_out << 8 | r_has_in << 12
+    uint32_t *tabs = keys + (size_t)W * cap;                      // [cap][TW]
+    uint16_t *gmask = reinterpret_cast<uint16_t *>(tabs + (size_t)TW * cap);   // has_in | has_out << 4 | l_has_out << 8 | r_has_in << 12
+    // count of entry x (0..15) of table t (0 cph, 1 ctn, 2 cht) of a slot
+    auto count_of = [&](const uint32_t *tb, int t, int x) -> unsigned {
+        return COMPACT ? (tb[t] >> (2 * x)) & 3u : reinterpret_cast<const unsigned char *>(tb)[16 * t + x];
+    };
     uint16_t *list = gmask + cap;
     __shared__ unsigned s_tile2[2], s_ndist;
     volatile uint32_t *vtag = tag;
     volatile uint32_t *vkeys = keys;
     if (*P.err & ERR_SLAB_OVERFLOW) return;
     for (unsigned i = tid; i < cap; i += COUNT_THREADS) tag[i] = TAG_EMPTY;
-    for (unsigned i = tid; i < 12 * cap; i += COUNT_THREADS) tabs[i] = 0;
+    for (unsigned i = tid; i < TW * cap; i += COUNT_THREADS) tabs[i] = 0;
     const unsigned n_tiles = P.t_hi - P.t_lo;
 
     auto load_key = [&](unsigned long long i, uint32_t (&key)[W], uint32_t &flags) {
@@ -218,22 +236,28 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_mercy(const MercyParams P) {
             if (slot == 0xFFFFFFFFu) continue;
             const uint32_t v0 = P.src[(uint64_t)W * P.cap + i];
             const int head = flags >> 3, tail = flags & 7, prev = (v0 >> 3) & 7, next = v0 & 7;
-            uint32_t *tb = tabs + (size_t)12 * slot;
-            if (prev < 4 && head < 4) { const int x = prev * 4 + head; sat_inc(tb + (x >> 2), x & 3); }
-            if (tail < 4 && next < 4) { const int x = tail * 4 + next; sat_inc(tb + 4 + (x >> 2), x & 3); }
-            if (head < 4 && tail < 4) { const int x = head * 4 + tail; sat_inc(tb + 8 + (x >> 2), x & 3); }
+            uint32_t *tb = tabs + (size_t)TW * slot;
+            if (COMPACT) {
+                if (prev < 4 && head < 4) sat_inc2(tb, prev * 4 + head);
+                if (tail < 4 && next < 4) sat_inc2(tb + 1, tail * 4 + next);
+                if (head < 4 && tail < 4) sat_inc2(tb + 2, head * 4 + tail);
+            } else {
+                if (prev < 4 && head < 4) { const int x = prev * 4 + head; sat_inc(tb + (x >> 2), x & 3); }
+                if (tail < 4 && next < 4) { const int x = tail * 4 + next; sat_inc(tb + 4 + (x >> 2), x & 3); }
+                if (head < 4 && tail < 4) { const int x = head * 4 + tail; sat_inc(tb + 8 + (x >> 2), x & 3); }
+            }
         }
         __syncthreads();
         // ---- phase C: group masks (s1.cpp:709-737)
         for (unsigned li = tid; li < nd; li += COUNT_THREADS) {
             const unsigned s = list[li];
-            const unsigned char *tb = reinterpret_cast<const unsigned char *>(tabs + (size_t)12 * s);
+            const uint32_t *tb = tabs + (size_t)TW * s;
             unsigned has_in = 0, has_out = 0, l_has_out = 0, r_has_in = 0;
             for (int j = 0; j < 4; ++j)
                 for (int x = 0; x < 4; ++x) {
-                    if (tb[x * 4 + j] >= P.m) has_in |= 1u << j;               // count_prev_head[x][j]
-                    if (tb[16 + j * 4 + x] >= P.m) has_out |= 1u << j;         // count_tail_next[j][x]
-                    if (tb[32 + j * 4 + x] >= P.m) { l_has_out |= 1u << j; r_has_in |= 1u << x; }
+                    if (count_of(tb, 0, x * 4 + j) >= P.m) has_in |= 1u << j;               // count_prev_head[x][j]
+                    if (count_of(tb, 1, j * 4 + x) >= P.m) has_out |= 1u << j;              // count_tail_next[j][x]
+                    if (count_of(tb, 2, j * 4 + x) >= P.m) { l_has_out |= 1u << j; r_has_in |= 1u << x; }
                 }
             gmask[s] = (uint16_t)(has_in | (has_out << 4) | (l_has_out << 8) | (r_has_in << 12));
         }
@@ -258,8 +282,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_mercy(const MercyParams P) {
                         const int head = flags >> 3, tail = flags & 7, strand = (v0 >> 6) & 1;
                         bool solid = false;
                         if (head < 4 && tail < 4) {
-                            const unsigned char *tb = reinterpret_cast<const unsigned char *>(tabs + (size_t)12 * slot);
-                            solid = tb[32 + head * 4 + tail] >= P.m;
+                            solid = count_of(tabs + (size_t)TW * slot, 2, head * 4 + tail) >= P.m;
                         }
                         s1_mercy_item(g, solid, head, tail, strand, kpos, [&](uint64_t pos, int flag) {
                             if (n_c < 2) c_val[n_c] = ((unsigned long long)pos << 2) | (unsigned)flag;
@@ -287,7 +310,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_mercy(const MercyParams P) {
         for (unsigned li = tid; li < nd; li += COUNT_THREADS) {
             const unsigned s = list[li];
             tag[s] = TAG_EMPTY;
-            for (int j = 0; j < 12; ++j) tabs[(size_t)12 * s + j] = 0;
+            for (int j = 0; j < TW; ++j) tabs[(size_t)TW * s + j] = 0;
         }
         __syncthreads();
     }

@@ -1344,6 +1344,9 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st, bool sharded = false) {
     if (ctx->n_positions == 0) { ctx->mercy_valid = true; return MGTA_OK; }
     // table: as many slots as one CTA can hold; tiles of mean <= cap / 2 ITEMS can never hold more than tab_limit distinct keys
     unsigned tab_cap = 4096;
+    // the table capacity (and with it the tile plan) is that of the byte tables; with min_count <= 3 the counts fit 2-bit
+    // fields, the same table takes a third of the shared memory and three CTAs share an SM
+    const bool compact = ctx->opt.min_count <= 3 && !getenv("MGTA_MERCY_BYTE_TABLES");
     while (tab_cap > 256 && mercy_smem_bytes(W, tab_cap) > 200 * 1024) tab_cap >>= 1;
     const unsigned tab_limit = tab_cap - 600;
     // tiles of mean <= 0.6 * cap ITEMS: even if every item were a distinct S a 6-sigma tile stays below tab_limit; a tile
@@ -1400,7 +1403,7 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st, bool sharded = false) {
         while (L.total + 3 * vec_bytes > budget && L.bins > 1) { n_batches *= 2; layout(n_batches); }
         if (L.total + 3 * vec_bytes > budget) FAIL(MGTA_ERR_MEM, "HBM budget %zu B cannot hold one level-1 bin of mercy items (%zu B)", budget, L.total);
         if ((rc = ensure_arena(ctx, L.total + 3 * vec_bytes))) return rc;
-        const size_t smem_m = mercy_smem_bytes(W, tab_cap);
+        const size_t smem_m = mercy_smem_bytes(W, tab_cap, compact);
         for (unsigned batch = 0; batch < n_batches && !retry; ++batch) {
             const unsigned b_lo = R_lo + batch * L.bins, b_hi = std::min(R_hi, b_lo + L.bins);
             if (b_lo >= b_hi) break;
@@ -1455,8 +1458,15 @@ int run_mercy(mgta_ctx *ctx, mgta_stage_stats *st, bool sharded = false) {
             {
                 cudaError_t e = cudaSuccess;
                 W_SWITCH(W, {
-                    e = cudaFuncSetAttribute(k_mercy<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
-                    if (e == cudaSuccess) k_mercy<WW><<<(unsigned)ctx->sm_count, COUNT_THREADS, smem_m, ctx->stream>>>(MP);
+                    int occ_m = 1;
+                    if (compact) {
+                        e = cudaFuncSetAttribute(k_mercy<WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+                        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, k_mercy<WW, true>, COUNT_THREADS, smem_m);
+                        if (e == cudaSuccess) k_mercy<WW, true><<<(unsigned)(ctx->sm_count * std::max(1, occ_m)), COUNT_THREADS, smem_m, ctx->stream>>>(MP);
+                    } else {
+                        e = cudaFuncSetAttribute(k_mercy<WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+                        if (e == cudaSuccess) k_mercy<WW, false><<<(unsigned)ctx->sm_count, COUNT_THREADS, smem_m, ctx->stream>>>(MP);
+                    }
                 });
                 if (e != cudaSuccess) FAIL(MGTA_ERR_CUDA, "k_mercy launch failed: %s", cudaGetErrorString(e));
             }
