@@ -126,17 +126,41 @@ __device__ __forceinline__ void bin_scatter(BinSmem &S, int n_slots, int IW, int
     }
     if (tid == 0) S.lbase[NB] = total;
     __syncthreads();
-    for (int i = tid; i < n_slots; i += PART_THREADS) {
-        const unsigned b = S.bin[i];
-        if (b != 0xFFFFu) S.perm[S.lbase[b] + S.rank[i]] = (uint16_t)i;
+    // Both loops are chains of dependent shared-memory reads (slot -> bin -> base -> words); four positions per thread are
+    // in flight at a time so that the chains overlap (the kernels ran at 50-60 % of the issue rate on short_scoreboard
+    // stalls with one chain per thread).
+    constexpr int UF = 4;
+    for (int i0 = tid; i0 < n_slots; i0 += UF * PART_THREADS) {
+        unsigned b_[UF], at_[UF];
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            const int i = i0 + u * PART_THREADS;
+            b_[u] = i < n_slots ? (unsigned)S.bin[i] : 0xFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < UF; ++u) at_[u] = b_[u] != 0xFFFFu ? S.lbase[b_[u]] + S.rank[i0 + u * PART_THREADS] : 0u;
+#pragma unroll
+        for (int u = 0; u < UF; ++u)
+            if (b_[u] != 0xFFFFu) S.perm[at_[u]] = (uint16_t)(i0 + u * PART_THREADS);
     }
     __syncthreads();
-    for (unsigned j = tid; j < total; j += PART_THREADS) {
-        const unsigned i = S.perm[j], b = S.bin[i];
-        const unsigned long long gb = S.gbase[b];                 // may have wrapped below zero (first index < sorted position): gb + j is exact
-        if (gb == 0x8000000000000000ull) continue;
-        uint32_t *d = dst + (gb + j);
-        for (int w = 0; w < IW; ++w, d += cap) *d = S.stage[w * P + i];
+    for (unsigned j0 = tid; j0 < total; j0 += UF * PART_THREADS) {
+        unsigned i_[UF];
+        unsigned long long gb_[UF];
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            const unsigned j = j0 + u * PART_THREADS;
+            i_[u] = j < total ? (unsigned)S.perm[j] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < UF; ++u)                               // gbase may have wrapped below zero (first index < sorted position): gb + j is exact
+            gb_[u] = i_[u] != 0xFFFFFFFFu ? S.gbase[S.bin[i_[u]]] : 0x8000000000000000ull;
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            if (gb_[u] == 0x8000000000000000ull) continue;
+            uint32_t *d = dst + (gb_[u] + (j0 + u * PART_THREADS));
+            for (int w = 0; w < IW; ++w, d += cap) *d = S.stage[w * P + i_[u]];
+        }
     }
     if (over) atomicOr(err, (unsigned)ERR_SLAB_OVERFLOW);
     __syncthreads();
@@ -176,7 +200,7 @@ struct EdgePartParams {
 
 // PW = payload words: 0 none, 1 = base position (u32), 2 = base position (lo, hi)
 template <int WE, int PW, int TP>
-__global__ void __launch_bounds__(PART_THREADS) k_edge_part(const EdgePartParams P) {
+__global__ void __launch_bounds__(PART_THREADS, TP == 4096 && WE + PW <= 2 ? 3 : 1) k_edge_part(const EdgePartParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int IW = WE + PW;
     constexpr int SW_WORDS = TP / 16 + WALK_BACK_WORDS + 12;
