@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+import oracle_memo as OM
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpu", "logic_host.cpp")
@@ -70,14 +71,14 @@ def test_device_logic_on_cpu_matches_oracle(logic, read_lib, ds, k, m, mercy):
     exp_solid = exp_ec = None
     exp_cands = np.empty(0, dtype=np.uint64)
     if m > 1:
-        exp_solid, exp_ec, exp_cands = O.stage1(rd, k, m, mercy)
+        exp_solid, exp_ec, exp_cands = OM.stage1(rd, k, m, mercy)
         assert np.array_equal(got["h1"], O.s1_hist(rd, k))
         assert np.array_equal(got["counting"], exp_ec)
         assert np.array_equal(got["cands"], exp_cands)
         if mercy:
             O.mercy(rd, k, exp_solid, exp_cands)
         assert np.array_equal(got["is_solid"][:len(exp_solid)], exp_solid)
-    stream, meta, totals = O.stage2(rd, k, m, exp_solid)
+    stream, meta, totals = OM.stage2(rd, k, m, exp_solid)
     assert np.array_equal(got["h2"], O.s2_hist(rd, k, m, exp_solid if exp_solid is not None else np.zeros(8, np.uint8)))
     assert got["stream"] == stream
     assert np.array_equal(got["meta"], meta)
@@ -113,7 +114,7 @@ def test_edge_centric_logic_matches_oracle(logic, read_lib, ds, k, m, mercy):
     n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
     exp_solid = None
     if m > 1:
-        exp_solid, exp_ec, cands = O.stage1(rd, k, m, mercy)
+        exp_solid, exp_ec, cands = OM.stage1(rd, k, m, mercy)
         got_solid = np.zeros(len(exp_solid) + 8, dtype=np.uint8)
         got_ec = np.zeros(65536, dtype=np.int64)
         assert lib_stage1_edges(logic, rd, k, m, got_solid, got_ec) == 0
@@ -121,7 +122,7 @@ def test_edge_centric_logic_matches_oracle(logic, read_lib, ds, k, m, mercy):
         assert np.array_equal(got_solid[:len(exp_solid)], exp_solid)
         if mercy:
             O.mercy(rd, k, exp_solid, cands)
-    exp = O.stage2(rd, k, m, exp_solid)
+    exp = OM.stage2(rd, k, m, exp_solid)
     # general mode: re-count under the (possibly mercy-extended) is_solid filter
     stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=False)
     assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
@@ -145,7 +146,7 @@ def test_device_mercy_scan_on_cpu_matches_oracle(logic, read_lib, ds, k, m):
     """cx1_emit.cuh mercy_scan_read (the code k_mercy_reads runs) over position flag vectors vs the oracle's restatement of
     s2_read_mercy_prepare over sorted candidates: same is_solid, same "Number mercy"."""
     _, rd = read_lib(ds)
-    solid, _, cands = O.stage1(rd, k, m, True)
+    solid, _, cands = OM.stage1(rd, k, m, True)
     exp = solid.copy()
     exp_n = O.mercy(rd, k, exp, cands)
     got = solid.copy()
@@ -165,10 +166,10 @@ def test_node_filter_drops_only_items_the_group_logic_drops(logic, read_lib, ds,
     _, rd = read_lib(ds)
     exp_solid = None
     if m > 1:
-        exp_solid, _, cands = O.stage1(rd, k, m, mercy)
+        exp_solid, _, cands = OM.stage1(rd, k, m, mercy)
         if mercy:
             O.mercy(rd, k, exp_solid, cands)
-    exp = O.stage2(rd, k, m, exp_solid)
+    exp = OM.stage2(rd, k, m, exp_solid)
     logic.logic_last_items.restype = ctypes.c_int64
     run_edges(logic, rd, k, m, exp_solid, fused=0)
     n_all = logic.logic_last_items()
@@ -189,10 +190,10 @@ def test_node_pass_reproduces_the_records(logic, read_lib, ds, k, m, mercy):
     _, rd = read_lib(ds)
     exp_solid = None
     if m > 1:
-        exp_solid, _, cands = O.stage1(rd, k, m, mercy)
+        exp_solid, _, cands = OM.stage1(rd, k, m, mercy)
         if mercy:
             O.mercy(rd, k, exp_solid, cands)
-    exp = O.stage2(rd, k, m, exp_solid)
+    exp = OM.stage2(rd, k, m, exp_solid)
     logic.logic_last_items.restype = ctypes.c_int64
     stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=4)
     assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
