@@ -172,7 +172,8 @@ def run_reference_arm(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if a.total_reads else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "reads_per_s": n / (ms / 1000.0),
-            "config": {"workload": workload_name(a, a.gpus), "genomes": n_genomes(a, a.gpus), "sample": sample, "sample_reads": n,
+            "config": {"workload": workload_name(a, a.gpus), "reads": a.reads_per_gpu * a.gpus, "read_len": a.read_len, "k": a.k,
+                       "min_count": a.m, "genomes": n_genomes(a, a.gpus), "sample": sample, "sample_reads": n,
                        "edges_per_step": edges, "sample_hashes": hashes},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "reads_per_s": n / (ms / 1000.0)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
