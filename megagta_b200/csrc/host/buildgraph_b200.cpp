@@ -300,6 +300,32 @@ int sink(void *user, int32_t b0, int32_t b1, const void *bytes, uint64_t n_bytes
     return 0;
 }
 
+// sdbg_info over all record files (sdbg_multi_io.h:160-187): num_threads = number of files, every row names its file;
+// empty buckets carry file_id -1 (the reader skips only those rows, :356-358).  -> total number of edges
+long long write_sdbg_info(const std::string &prefix, int kmer_k, const std::vector<const Writer *> &files) {
+    const int wpt = (2 * kmer_k + 31) / 32;
+    FILE *info = fopen((prefix + ".sdbg_info").c_str(), "w");
+    if (!info) die("cannot write " + prefix + ".sdbg_info");
+    long long te = 0, tt = 0, tl = 0;
+    for (const Writer *W : files)
+        for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) { te += W->n_items[b]; tt += W->n_tips[b]; tl += W->n_large[b]; }
+    fprintf(info, "k %d\n", kmer_k);
+    fprintf(info, "words_per_tip_label %d\n", wpt);
+    fprintf(info, "num_buckets %d\n", MGTA_NUM_BUCKETS);
+    fprintf(info, "num_threads %d\n", (int)files.size());
+    fprintf(info, "total_size %lld\n", te);
+    fprintf(info, "num_tips %lld\n", tt);
+    fprintf(info, "large_multi %lld\n", tl);
+    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) {
+        const Writer *own = nullptr;
+        for (const Writer *W : files) if (W->n_items[b]) { if (own) die("internal: bucket " + std::to_string(b) + " emitted by two GPUs"); own = W; }
+        if (own) fprintf(info, "%d %d %lld %lld %lld %lld\n", b, (int)own->fid[b], own->start[b], own->n_items[b], own->n_tips[b], own->n_large[b]);
+        else fprintf(info, "%d %d %lld %lld %lld %lld\n", b, -1, 0LL, 0LL, 0LL, 0LL);
+    }
+    fclose(info);
+    return te;
+}
+
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 [[noreturn]] void die_now(const std::string &msg) {            // from a GPU thread: the other threads may sit in a collective
@@ -481,27 +507,9 @@ int build_graph(int argc, char **argv) {
         if (opt.need_mercy) fprintf(stderr, "[B200] Number mercy: %llu\n", (unsigned long long)jobs[0].num_mercy);   // s2.cpp:241
     }
 
-    // sdbg_info over all files (sdbg_multi_io.h:160-187): num_threads = number of files, every row names its file
-    const int wpt = (2 * opt.kmer_k + 31) / 32;
-    FILE *info = fopen((opt.output_prefix + ".sdbg_info").c_str(), "w");
-    if (!info) die("cannot write " + opt.output_prefix + ".sdbg_info");
-    long long te = 0, tt = 0, tl = 0;
-    for (auto &J : jobs)
-        for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) { te += J.W.n_items[b]; tt += J.W.n_tips[b]; tl += J.W.n_large[b]; }
-    fprintf(info, "k %d\n", opt.kmer_k);
-    fprintf(info, "words_per_tip_label %d\n", wpt);
-    fprintf(info, "num_buckets %d\n", MGTA_NUM_BUCKETS);
-    fprintf(info, "num_threads %d\n", G);
-    fprintf(info, "total_size %lld\n", te);
-    fprintf(info, "num_tips %lld\n", tt);
-    fprintf(info, "large_multi %lld\n", tl);
-    for (int b = 0; b < MGTA_NUM_BUCKETS; ++b) {
-        const GpuJob *own = nullptr;
-        for (auto &J : jobs) if (J.W.n_items[b]) { if (own) die("internal: bucket " + std::to_string(b) + " emitted by two GPUs"); own = &J; }
-        if (own) fprintf(info, "%d %d %lld %lld %lld %lld\n", b, (int)own->W.fid[b], own->W.start[b], own->W.n_items[b], own->W.n_tips[b], own->W.n_large[b]);
-        else fprintf(info, "%d %d %lld %lld %lld %lld\n", b, -1, 0LL, 0LL, 0LL, 0LL);
-    }
-    fclose(info);
+    std::vector<const Writer *> files;
+    for (auto &J : jobs) files.push_back(&J.W);
+    const long long te = write_sdbg_info(opt.output_prefix, opt.kmer_k, files);
 
     for (auto &J : jobs)
         fprintf(stderr, "[B200] GPU %d: reads on the device in %.2f s; stage 1 %.1f ms device (%llu items) / %.2f s wall; stage 2 %.1f ms device "
