@@ -8,7 +8,7 @@
  * `CX1::run()` (src/cx1.h:443-623).  The only historic GPU seam is the undeclared
  * `lv2_gpu_sort(...)` / `alloc_gpu_buffers` / `free_gpu_buffers` under `#ifdef USE_GPU`
  * (src/cx1_read2sdbg_s1.cpp:308,619,945; src/cx1_read2sdbg_s2.cpp:391,697,926).  A host
- * `build_graph()` replacement (megagta_b200/csrc/host/build_graph_b200.cpp) keeps the reference's
+ * `build_graph()` replacement (megagta_b200/csrc/host/buildgraph_b200.cpp) keeps the reference's
  * option table, read-library loader and output writer and calls the entry points below; see
  * INTEGRATION.md for the patch a reference maintainer would apply.
  *
@@ -135,7 +135,8 @@ int mgta_solid_device_buffer(mgta_ctx *ctx, void **dev_ptr, uint64_t *n_bytes);
 int mgta_get_is_solid(mgta_ctx *ctx, uint8_t *host, uint64_t n_bytes);
 int mgta_set_is_solid(mgta_ctx *ctx, const uint8_t *host, uint64_t n_bytes);
 
-/* Mercy edges (opts.need_mercy, min_count > 1, world == 1): mgta_stage1 then also (a) emits the mercy candidates of
+/* Mercy edges (opts.need_mercy, min_count > 1; on one shard through mgta_stage1, on several through the sharded build
+ * below, which exchanges the candidates): stage 1 then also (a) emits the mercy candidates of
  * s1_lv2_output_ (s1.cpp:762-826: packed ((start_idx + kmer_offset) << 2) | flag; the reference spreads them over
  * <prefix>.mercy_cand.N files, here they stay on the device) and (b) runs the per-read scan of s2_read_mercy_prepare
  * (s2.cpp:106-250) that extends is_solid; mgta_stage2 then builds the graph from the extended vector.
