@@ -18,6 +18,9 @@
 #include <zlib.h>
 #include <omp.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <chrono>
 #include <stdexcept>
 #include <string>
@@ -129,6 +132,59 @@ struct Reads {
     }
 };
 
+// the 16 bases of a packed word in reverse order (2-bit groups swapped end to end)
+inline uint32_t reverse_bases(uint32_t x) {
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    return __builtin_bswap32(x);
+}
+
+// The records of <prefix>.bin in memory.  A plain file is mapped (the records are read where the page cache holds them);
+// a gzip'ed one is inflated in large blocks -- zlib decides which it is, as in the reference (gzread, sequence_manager.cpp:186-196).
+struct BinFile {
+    const uint32_t *words = nullptr;
+    size_t n_words = 0, tail_bytes = 0;        // tail_bytes: bytes after the last whole word (a truncated file)
+    void *map = nullptr;
+    size_t map_len = 0;
+    std::vector<uint32_t> inflated;
+    void open(const std::string &path) {
+        gzFile gz = gzopen(path.c_str(), "rb");
+        if (!gz) die("cannot open " + path);
+        if (gzdirect(gz)) {                                          // not compressed
+            gzclose(gz);
+            const int fd = ::open(path.c_str(), O_RDONLY);
+            struct stat sb;
+            if (fd < 0 || fstat(fd, &sb) != 0) die("cannot open " + path + ": " + strerror(errno));
+            map_len = (size_t)sb.st_size;
+            if (map_len) {
+                map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (map == MAP_FAILED) die("cannot map " + path + ": " + strerror(errno));
+                madvise(map, map_len, MADV_WILLNEED);
+            }
+            ::close(fd);
+            words = (const uint32_t *)map; n_words = map_len / 4; tail_bytes = map_len % 4;
+            return;
+        }
+        gzbuffer(gz, 1 << 22);
+        size_t bytes = 0;
+        for (;;) {
+            const size_t block = (size_t)64 << 20;
+            inflated.resize((bytes + block + 3) / 4);
+            const int got = gzread(gz, (char *)inflated.data() + bytes, (unsigned)block);
+            if (got < 0) die("cannot inflate " + path);
+            bytes += (size_t)got;
+            if ((size_t)got < block) break;
+        }
+        gzclose(gz);
+        words = inflated.data(); n_words = bytes / 4; tail_bytes = bytes % 4;
+    }
+    void close() {
+        if (map && map_len) munmap(map, map_len);
+        map = nullptr;
+        std::vector<uint32_t>().swap(inflated);
+    }
+};
+
 Reads load_read_lib(const std::string &prefix, int threads, bool want_pinned) {
     Reads R;
     long long total_bases = 0, num_reads = 0;
@@ -138,32 +194,25 @@ Reads load_read_lib(const std::string &prefix, int threads, bool want_pinned) {
         if (fscanf(f, "%lld %lld", &total_bases, &num_reads) != 2) die("bad first line in " + prefix + ".lib_info");
         fclose(f);
     }
-    gzFile gz = gzopen((prefix + ".bin").c_str(), "rb");        // the reference reads .bin through gzread, too
-    if (!gz) die("cannot open " + prefix + ".bin");
-    gzbuffer(gz, 1 << 22);
-    // pass 1: raw records into memory (u32 len, ceil(len/16) words, forward orientation), offsets per read
-    std::vector<uint32_t> raw;
-    raw.reserve((size_t)(total_bases / 16 + 2 * num_reads + 16));
+    BinFile bin;
+    bin.open(prefix + ".bin");
+    // pass 1: where every record lies (u32 len, ceil(len/16) words, forward orientation)
     std::vector<uint64_t> rec_off;
     rec_off.reserve((size_t)num_reads);
     R.start.reserve((size_t)num_reads + 1);
     R.start.push_back(0);
     uint64_t bases = 0;
-    for (;;) {
-        uint32_t len;
-        int got = gzread(gz, &len, 4);
-        if (got == 0) break;
-        if (got != 4) die("truncated record header in " + prefix + ".bin");
-        const uint32_t nw = (len + 15) / 16;
-        const size_t at = raw.size();
-        raw.resize(at + nw);
-        if (nw && gzread(gz, raw.data() + at, nw * 4) != (int)(nw * 4)) die("truncated record in " + prefix + ".bin");
-        rec_off.push_back(at);
+    for (size_t at = 0; at < bin.n_words;) {
+        const uint32_t len = bin.words[at];
+        const size_t nw = ((size_t)len + 15) / 16;
+        if (at + 1 + nw > bin.n_words) die("truncated record in " + prefix + ".bin");
+        rec_off.push_back(at + 1);
         bases += len;
         R.start.push_back(bases);
         R.max_len = std::max<int>(R.max_len, (int)len);
+        at += 1 + nw;
     }
-    gzclose(gz);
+    if (bin.tail_bytes) die("truncated record header in " + prefix + ".bin");
     R.n_reads = rec_off.size();
     if ((long long)R.n_reads != num_reads || (long long)bases != total_bases)
         die("read library " + prefix + ": .bin holds " + std::to_string(R.n_reads) + " reads / " + std::to_string(bases) +
@@ -171,26 +220,38 @@ Reads load_read_lib(const std::string &prefix, int threads, bool want_pinned) {
     R.n_words = bases / 16 + 1;
     R.alloc(R.n_words, want_pinned);
     if (!R.seq) die("out of host memory for the packed reads");
-    // pass 2: reverse each read into its bit range; reads are independent except for shared boundary words (atomic OR)
+    // pass 2: every read reversed (not complemented) into its bit range, a word at a time: the record's words in reverse
+    // order with their bases reversed are the reversed read behind `pad` empty slots; they stream through a 64-bit
+    // accumulator that is aligned with the destination.  Only the first and the last destination word can be shared with the
+    // neighbouring reads (atomic OR into the zeroed buffer); the words in between belong to this read alone.
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
     for (long long r = 0; r < (long long)R.n_reads; ++r) {
-        const uint32_t *w = raw.data() + rec_off[(size_t)r];
+        const uint32_t *w = bin.words + rec_off[(size_t)r];
         const uint64_t s = R.start[(size_t)r];
         const int L = (int)(R.start[(size_t)r + 1] - s);
-        uint64_t g = s;
-        uint32_t acc = 0;
-        int filled = (int)(g & 15);                            // bases already belonging to other reads in the first word
-        uint64_t word = g >> 4;
-        for (int i = L - 1; i >= 0; --i) {                     // reversed, not complemented
-            const uint32_t c = (w[i >> 4] >> ((15 - (i & 15)) * 2)) & 3u;
-            acc |= c << ((15 - filled) * 2);
-            if (++filled == 16) {
-                __atomic_fetch_or(&R.seq[word], acc, __ATOMIC_RELAXED);
-                acc = 0; filled = 0; ++word;
+        if (L == 0) continue;
+        const int nw = (L + 15) / 16, pad = nw * 16 - L;
+        uint64_t word = s >> 4;
+        const uint64_t last_word = (s + (uint64_t)L - 1) >> 4;
+        uint64_t acc = 0;
+        int nbits = (int)(s & 15) * 2;                         // bits of the first word that belong to earlier reads
+        for (int m = 0; m < nw; ++m) {
+            const uint32_t v = reverse_bases(w[nw - 1 - m]);
+            const int nb = m == 0 ? 32 - 2 * pad : 32;         // the first reversed word starts with the padding slots
+            acc = (acc << nb) | (nb == 32 ? (uint64_t)v : (uint64_t)(v & ((1u << nb) - 1u)));
+            nbits += nb;
+            if (nbits >= 32) {
+                const uint32_t out = (uint32_t)(acc >> (nbits - 32));
+                nbits -= 32;
+                acc &= nbits ? ((1ull << nbits) - 1ull) : 0ull;
+                if (word == (s >> 4) || word == last_word) __atomic_fetch_or(&R.seq[word], out, __ATOMIC_RELAXED);
+                else R.seq[word] = out;
+                ++word;
             }
         }
-        if (filled) __atomic_fetch_or(&R.seq[word], acc, __ATOMIC_RELAXED);
+        if (nbits) __atomic_fetch_or(&R.seq[word], (uint32_t)(acc << (32 - nbits)), __ATOMIC_RELAXED);
     }
+    bin.close();
     return R;
 }
 

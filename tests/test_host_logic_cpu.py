@@ -73,6 +73,46 @@ def test_driver_loader_packs_the_reads_like_the_oracle(host, read_lib, ds):
     assert len(got["seq"]) == n and np.array_equal(got["seq"], rd["seq"][:n])
 
 
+def test_driver_loader_on_ragged_and_gzipped_libraries(host, tmp_path):
+    """lengths 0..90 in random order (every alignment of a read against the word grid, empty reads, reads inside one word),
+    once as a plain .bin (mapped) and once gzip'ed (inflated through zlib, as the reference reads it)"""
+    from megagta_b200 import synth
+    rng = np.random.default_rng(17)
+    reads = [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(0, 91, 6000)]
+    reads += [rng.integers(0, 4, n, dtype=np.uint8) for n in (0, 0, 1, 15, 16, 17, 31, 32, 33, 1000, 4097)]
+    prefix = str(tmp_path / "ragged")
+    synth.write_variable_reads(prefix, reads)
+    rd = O.load_read_lib(prefix)
+    got, _ = load_reads(host, prefix)
+    n = int(rd["start"][-1]) // 16 + 1
+    assert got["n_reads"] == len(reads) and got["max_len"] == 4097
+    assert np.array_equal(got["start"], rd["start"]) and np.array_equal(got["seq"], rd["seq"][:n])
+    gz = str(tmp_path / "ragged_gz")
+    with gzip.open(gz + ".bin", "wb") as f:
+        f.write(open(prefix + ".bin", "rb").read())
+    open(gz + ".lib_info", "w").write(open(prefix + ".lib_info").read())
+    got_gz, _ = load_reads(host, gz)
+    assert np.array_equal(got_gz["start"], got["start"]) and np.array_equal(got_gz["seq"], got["seq"])
+
+
+@pytest.mark.parametrize("cut,msg", [(-3, "truncated record in"), (-8, "truncated record in"), (2, "truncated record header"), (None, ".lib_info says")])
+def test_driver_loader_rejects_damaged_libraries(host, read_lib, tmp_path, cut, msg):
+    prefix, _ = read_lib("tiny")
+    bad = str(tmp_path / "bad")
+    raw = open(prefix + ".bin", "rb").read()
+    open(bad + ".bin", "wb").write(raw if cut is None else raw[:cut] if cut < 0 else raw + b"\x07" * cut)
+    info = open(prefix + ".lib_info").read()
+    if cut is None:
+        first, rest = info.split("\n", 1)
+        info = "%d %d\n%s" % (int(first.split()[0]) + 1, int(first.split()[1]), rest)
+    open(bad + ".lib_info", "w").write(info)
+    code = ("import ctypes; l = ctypes.CDLL(%r); p = ctypes.c_void_p(); q = ctypes.c_void_p(); a = ctypes.c_uint64(); b = ctypes.c_uint64(); "
+            "m = ctypes.c_int(); l.hd_load_reads(%r, b'', 2, ctypes.byref(p), ctypes.byref(a), ctypes.byref(q), ctypes.byref(m), ctypes.byref(b))"
+            % (OUT, bad.encode()))
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "[ERROR]" in r.stderr and msg in r.stderr, r.stderr
+
+
 @pytest.mark.parametrize("ds", ["smoke", "adversarial"])
 def test_driver_appends_assist_reads_like_the_oracle(host, read_lib, data_dir, ds):
     prefix, rd = read_lib(ds)
