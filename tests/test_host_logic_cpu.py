@@ -63,7 +63,7 @@ def load_reads(host, prefix, assist=""):
     return dict(seq=s, start=t, n_reads=int(n), max_len=max_len.value), int(n_short.value)
 
 
-@pytest.mark.parametrize("ds", ["tiny", "smoke", "adversarial", "xander"])
+@pytest.mark.parametrize("ds", ["tiny", "smoke", "adversarial", "xander", "meta200k"])
 def test_driver_loader_packs_the_reads_like_the_oracle(host, read_lib, ds):
     prefix, rd = read_lib(ds)
     got, n_short = load_reads(host, prefix)
