@@ -39,3 +39,27 @@ def test_no_device_means_an_error_not_a_fallback():
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(cabi.MgtaError):                            # the index builder has no CPU path either
         cabi.Sdbg(31)
+
+
+def test_ctypes_structs_have_the_layout_of_the_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the boundary, as a C compiler sees include/mgta_cuda.h, against the
+    ctypes mirror in cabi.py (a silent mismatch would shift every field after it)"""
+    import subprocess
+    structs = {"mgta_opts": cabi.Opts, "mgta_stage_stats": cabi.StageStats, "mgta_collective": cabi.Collective,
+               "mgta_sdbg_header_t": cabi.SdbgHeader}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mgta_cuda.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, (name, field)
+    assert cabi.COLL_ALL_REDUCE_SUM_U64 == 4 and cabi.SDBG_TIP_MAJOR == 23 and cabi.SDBG_TIP_SEQ == 8
