@@ -8,6 +8,7 @@
 #define private public
 #include "succinct_dbg.h"
 #undef private
+#include "cx1_read2sdbg.h"
 int build_lib(int argc, char **argv);
 int build_graph(int argc, char **argv);
 int main_assemble(int argc, char **argv);
@@ -82,7 +83,29 @@ static int sdbg_dump(int argc, char **argv) {
     return 0;
 }
 
+
+// readsdump <read_lib_prefix> <assist_seq or ""> <out>: the read set as the reference holds it in memory after its own
+// s1_read_input_prepare (cx1_read2sdbg_s1.cpp:96-175: ReadBinaryLibs with is_reverse = true, then --assist_seq appended) --
+// the two arrays the C ABI's mgta_set_reads takes.  Pins the oracle's numpy loader and the driver's C++ loader.
+static int reads_dump(int argc, char **argv) {
+    if (argc < 4) { fprintf(stderr, "usage: readsdump <read_lib_prefix> <assist_seq|\"\"> <out>\n"); return 1; }
+    cx1_read2sdbg::read2sdbg_global_t *g = new cx1_read2sdbg::read2sdbg_global_t();
+    g->kmer_k = 21; g->kmer_freq_threshold = 1; g->host_mem = (int64_t)1 << 40; g->gpu_mem = 0; g->num_cpu_threads = 2;
+    g->num_output_threads = 1; g->mem_flag = 1; g->need_mercy = false;
+    g->read_lib_file = argv[1]; g->assist_seq_file = argv[2]; g->output_prefix = argv[3];
+    cx1_read2sdbg::s1::s1_read_input_prepare(*g);
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 1;
+    int64_t hdr[4] = {g->num_reads, g->num_short_reads, g->max_read_length, (int64_t)g->package.base_size()};
+    put(f, "hdr", hdr, sizeof(hdr));
+    put(f, "packed_seq", &g->package.packed_seq[0], g->package.packed_seq.size() * 4);
+    put(f, "start_idx", &g->package.start_idx_[0], g->package.start_idx_.size() * 8);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 2 && strcmp(argv[1], "readsdump") == 0) return reads_dump(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "sdbgdump") == 0) return sdbg_dump(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "buildlib") == 0) return build_lib(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "buildgraph") == 0) return build_graph(argc - 1, argv + 1);

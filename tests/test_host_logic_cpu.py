@@ -73,6 +73,33 @@ def test_driver_loader_packs_the_reads_like_the_oracle(host, read_lib, ds):
     assert len(got["seq"]) == n and np.array_equal(got["seq"], rd["seq"][:n])
 
 
+@pytest.mark.parametrize("ds,assist", [("tiny", False), ("smoke", True), ("adversarial", True), ("xander", False)])
+def test_loaders_equal_the_reference_sequence_package(host, read_lib, data_dir, tmp_path, ds, assist):
+    """the read set as the UNMODIFIED reference holds it in memory after its own s1_read_input_prepare (`megagta_ref readsdump`:
+    ReadBinaryLibs with is_reverse = true, --assist_seq appended; cx1_read2sdbg_s1.cpp:96-134) = what the oracle's numpy loader
+    builds = what the driver's C++ loader hands to mgta_set_reads, bit for bit"""
+    if not O.have_ref() or "readsdump" not in open(O.REF_BIN, "rb").read().decode("latin1"):
+        pytest.skip("oracle/_ref/megagta_ref with readsdump not built")
+    from oracle import sdbg_oracle as SO
+    prefix, rd = read_lib(ds)
+    fa = datasets.assist_fasta(ds, data_dir) if assist else ""
+    dump = str(tmp_path / "reads.dump")
+    r = subprocess.run([O.REF_BIN, "readsdump", prefix, fa, dump], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    d = SO.read_dump(dump)
+    n_reads, n_short, max_len, bases = (int(x) for x in np.frombuffer(d["hdr"], np.int64))
+    ref_seq, ref_start = np.frombuffer(d["packed_seq"], np.uint32), np.frombuffer(d["start_idx"], np.uint64)
+    exp, n0 = O.with_assist(rd, fa) if assist else (rd, rd["n_reads"])
+    got, got_short = load_reads(host, prefix, fa)
+    n = bases // 16 + 1
+    assert len(ref_seq) == n                                          # the n_words the ABI is given
+    for name, x in (("oracle", exp), ("driver", got)):
+        assert x["n_reads"] == n_reads and x["max_len"] == max_len, name
+        assert np.array_equal(x["start"], ref_start), name
+        assert np.array_equal(x["seq"][:n], ref_seq), name
+    assert n0 == n_short == got_short
+
+
 def test_driver_loader_on_ragged_and_gzipped_libraries(host, tmp_path):
     """lengths 0..90 in random order (every alignment of a read against the word grid, empty reads, reads inside one word),
     once as a plain .bin (mapped) and once gzip'ed (inflated through zlib, as the reference reads it)"""
