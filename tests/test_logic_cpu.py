@@ -105,7 +105,10 @@ EDGE_CASES = [("tiny", 21, 1, False), ("tiny", 25, 2, True), ("tiny", 13, 2, Fal
               ("smoke", 15, 2, False), ("smoke", 47, 2, False),
               ("adversarial", 31, 2, True), ("adversarial", 17, 2, False), ("adversarial", 48, 2, False),
               ("adversarial", 27, 3, True), ("adversarial", 64, 2, True), ("adversarial", 21, 1, False),
-              ("xander", 29, 1, False), ("xander", 44, 2, True)]
+              ("xander", 29, 1, False), ("xander", 44, 2, True),
+              # the ends of the k range (MGTA_MAX_K = 127, bucket prefix needs k >= 9) and word-boundary sizes of 8-word k-mers
+              ("xander", 127, 1, False), ("xander", 126, 2, False), ("xander", 112, 2, True), ("xander", 97, 3, True),
+              ("tiny", 10, 2, False), ("tiny", 11, 1, False)]
 
 
 @pytest.mark.parametrize("ds,k,m,mercy", EDGE_CASES)
