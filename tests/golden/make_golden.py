@@ -25,12 +25,12 @@ CASES = []
 for k, m, mercy in [(31, 2, False), (31, 2, True), (21, 2, False), (22, 2, False), (32, 2, False), (41, 2, False),
                     (61, 2, False), (99, 2, False), (31, 1, False), (31, 3, False), (27, 3, True)]:
     CASES.append(("smoke", k, m, mercy))
-for k, m, mercy in [(29, 1, False), (44, 1, False), (29, 2, True)]:
+for k, m, mercy in [(29, 1, False), (44, 1, False), (29, 2, True), (127, 1, False), (126, 2, False), (112, 2, True)]:   # 127 = kMaxK
     CASES.append(("xander", k, m, mercy))
 for k, m, mercy in [(31, 2, False), (21, 1, False), (27, 3, False), (30, 2, False), (31, 2, True), (27, 3, True),
                     (48, 2, False), (17, 2, False)]:
     CASES.append(("adversarial", k, m, mercy))
-for k, m, mercy in [(21, 1, False), (25, 2, False), (25, 2, True)]:
+for k, m, mercy in [(21, 1, False), (25, 2, False), (25, 2, True), (10, 2, False), (11, 1, False)]:
     CASES.append(("tiny", k, m, mercy))
 for k, m, mercy in [(31, 2, False), (61, 2, False), (21, 3, False)]:
     CASES.append(("meta200k", k, m, mercy))

@@ -14,6 +14,7 @@ FAST_CASES = [
     "xander_k29_m1", "xander_k44_m1", "xander_k29_m2_mercy",
     "adversarial_k31_m2", "adversarial_k21_m1", "adversarial_k27_m3", "adversarial_k30_m2",
     "adversarial_k31_m2_mercy", "adversarial_k27_m3_mercy", "adversarial_k48_m2", "adversarial_k17_m2",
+    "xander_k127_m1", "xander_k126_m2", "xander_k112_m2_mercy", "tiny_k10_m2", "tiny_k11_m1",      # the ends of the k range (kMaxK = 127)
 ]
 
 
