@@ -66,3 +66,20 @@ def test_level2_sink_replays_the_records_through_the_reference_writer(read_lib, 
     bad.tofile(mf)
     r = subprocess.run([O.REF_BIN, "replaysink", sf, mf, str(k), str(tmp_path / "bad"), str(per)], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0
+
+
+def test_level1_patch_applies_to_the_reference_driver(tmp_path):
+    """integration/megagta_py_level1.patch (INTEGRATION.md Level 1: `--b200-bin` / $MEGAGTA_B200 swaps the executable of the
+    buildlib, buildgraph and findstart steps) applies to the reference's megagta.py as it is, and the result still parses"""
+    import shutil
+    src = "/root/reference/src/megagta.py"
+    if not os.path.exists(src) or not shutil.which("patch"):
+        pytest.skip("the reference tree (or patch) is not present")
+    os.makedirs(str(tmp_path / "src"))
+    shutil.copy(src, str(tmp_path / "src" / "megagta.py"))
+    r = subprocess.run(["patch", "-p1", "-i", os.path.join(ROOT, "integration", "megagta_py_level1.patch")], cwd=str(tmp_path),
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "FAILED" not in r.stdout and "fuzz" not in r.stdout, r.stdout + r.stderr
+    text = open(str(tmp_path / "src" / "megagta.py")).read()
+    compile(text, "megagta.py", "exec")
+    assert text.count('sub_program("') == 3 and '[opt.bin_dir + "megagta", "buildgraph"]' not in text
