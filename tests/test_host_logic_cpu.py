@@ -100,6 +100,41 @@ def test_loaders_equal_the_reference_sequence_package(host, read_lib, data_dir, 
     assert n0 == n_short == got_short
 
 
+ASSIST_EDGE_FILES = {
+    "multi_line_fasta": ">c0 some text\nACGTNacgtnACGTACGTACGTACGTACGTACGTACGT\nacgtacgtacgtnnnnACGT\nAC\n>c1\nGGGGCCCCAAAATTTTGGGGCCCCAAAATTTTG\n",
+    "crlf_fasta": ">c0\r\nACGTACGTACGTACGTACGTACGTACGTACGTAC\r\nGGGTTT\r\n>c1\r\nTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT\r\n",
+    "fastq_with_marker_qualities": "@a\nACGTACGTACGTACGTACGTACGTAAAA\nCCCCGGGGTTTTACGTACGTACGTACGT\n+a\n@IIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+                                   ">IIIIIIIIIIIIIIIIIIIIIIIIIII\n@b\nACGTACGTACGTACGTACGTACGTACGTAA\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n",
+    "blank_lines": "\n\n>a\n\nACGTACGTACGTACGTACGTACGTACGTACGT\n\nACGT\n\n>b\nACGTACGTACGTACGTACGTACGTACGTACGTTT\n\n",
+    "no_final_newline": ">a\nACGTACGTACGTACGTACGTACGTACGTACGT\n>b\nACGTACGTACGTACGTACGTACGTACGTACGTTT",
+    "empty_records": ">a\n>b\nACGTACGTACGTACGTACGTACGTACGTACGTTT\n>c\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(ASSIST_EDGE_FILES))
+def test_assist_parser_equals_the_reference_on_edge_case_files(host, read_lib, tmp_path, name):
+    """--assist_seq files the reference reads through kseq (s1.cpp:120-134): multi-line and CRLF FASTA, FASTQ whose quality
+    lines start with '@' / '>', blank lines, no final newline, empty records -- the driver's append_assist against the
+    reference's own SequencePackage (`megagta_ref readsdump`)"""
+    if not O.have_ref() or "readsdump" not in open(O.REF_BIN, "rb").read().decode("latin1"):
+        pytest.skip("oracle/_ref/megagta_ref with readsdump not built")
+    from oracle import sdbg_oracle as SO
+    prefix, rd = read_lib("tiny")
+    fa = str(tmp_path / (name + ".fx"))
+    open(fa, "w", newline="").write(ASSIST_EDGE_FILES[name])
+    open(fa + ".info", "w").write("0 0\n")                           # only its presence matters to either loader
+    dump = str(tmp_path / "reads.dump")
+    r = subprocess.run([O.REF_BIN, "readsdump", prefix, fa, dump], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    d = SO.read_dump(dump)
+    ref_seq, ref_start = np.frombuffer(d["packed_seq"], np.uint32), np.frombuffer(d["start_idx"], np.uint64)
+    got, n_short = load_reads(host, prefix, fa)
+    assert n_short == rd["n_reads"] and got["n_reads"] == len(ref_start) - 1 > n_short
+    assert np.array_equal(got["start"], ref_start)
+    n = int(ref_start[-1]) // 16 + 1
+    assert np.array_equal(got["seq"][:n], ref_seq[:n])
+
+
 def test_driver_loader_on_ragged_and_gzipped_libraries(host, tmp_path):
     """lengths 0..90 in random order (every alignment of a read against the word grid, empty reads, reads inside one word),
     once as a plain .bin (mapped) and once gzip'ed (inflated through zlib, as the reference reads it)"""
