@@ -18,6 +18,7 @@ import numpy as np
 import pytest
 
 import datasets
+import fastx_cases
 import oracle_memo as OM
 from megagta_b200 import sdbg_io
 from oracle import oracle as O
@@ -258,18 +259,7 @@ def test_fastx_reader_follows_the_kseq_rules(host, tmp_path):
         path = os.path.join(d, f)
         want = ST.fastx_sequences(path)
         assert len(want) > 1000 and fastx(host, path) == want
-    edge = {
-        "empty.fa": b"",
-        "no_newline.fa": b">a\nACGT\n>b x y\nAC\nGT",
-        "header_only.fa": b">a\n>b\nAC\n>c",
-        "blank_lines.fa": b"\n\n>a\n\nAC\n\nGT\n\n>b\n\n",
-        "crlf.fq": b"@a\r\nACGT\r\n+\r\nIIII\r\n@b\r\nAC\r\n+\r\nII\r\n",
-        "multi.fq": b"@a\nACGT\nACG\n+a\n@III\n>II\n@b\nA\n+\nI\n",
-        "truncated.fq": b"@a\nACGT\n+\nIIII\n@b\nACGT\n+\nII",
-        "no_qual.fq": b"@a\nACGT\n+\nIIII\n@b\nACGT\n+",
-        "junk_first.fa": b"junk line\nmore junk\n>a\nACGT\n",
-        "mixed.fx": b">a\nACGT\n@b\nACGT\n+\nIIII\n>c\nAC\n",
-    }
+    edge = fastx_cases.EDGE
     for name, data in edge.items():
         path = os.path.join(d, name)
         open(path, "wb").write(data)

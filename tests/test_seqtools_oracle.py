@@ -9,6 +9,7 @@ import os
 import pytest
 
 import datasets
+import fastx_cases
 from oracle import oracle as O
 from oracle import seqtools_oracle as ST
 
@@ -26,6 +27,23 @@ def test_buildlib_oracle_equals_the_reference_binary(tmp_path):
     if not O.have_ref():
         pytest.skip("oracle/_ref/megagta_ref not built")
     lib = _load("test_gpu_buildlib").write_inputs(str(tmp_path))
+    ref = str(tmp_path / "ref")
+    O.run_ref_buildlib(lib, ref)
+    bin_bytes, info = ST.buildlib(lib)
+    assert info == open(ref + ".lib_info").read()
+    assert bin_bytes == open(ref + ".bin", "rb").read()
+
+
+@pytest.mark.parametrize("name", sorted(fastx_cases.EDGE))
+def test_buildlib_oracle_equals_the_reference_on_edge_case_files(tmp_path, name):
+    """empty file, no final newline, header-only records, blank lines, CRLF FASTQ, multi-line FASTQ with '@' / '>' quality
+    lines, truncated / missing quality, junk before the first header, FASTA and FASTQ records mixed"""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/megagta_ref not built")
+    path = str(tmp_path / name)
+    open(path, "wb").write(fastx_cases.EDGE[name])
+    lib = str(tmp_path / "x.lib")
+    open(lib, "w").write("edge case\nse %s\n" % path)
     ref = str(tmp_path / "ref")
     O.run_ref_buildlib(lib, ref)
     bin_bytes, info = ST.buildlib(lib)
