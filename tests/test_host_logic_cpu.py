@@ -298,3 +298,22 @@ def test_model_kmers_follow_the_generator_rules(host, tmp_path, k):
             else:
                 w1 = (w1 << 5) | code[c]
         assert (int(r[i, 0]), int(r[i, 1])) == (w0, w1)
+
+
+@pytest.mark.parametrize("gene", ["nifH", "rplB", "nirK", "nosZ"])
+def test_model_kmers_on_the_reference_gene_alignments(host, gene):
+    """findstart's host rules on the reference's own aligned gene families (present in this container only)"""
+    faa = "/root/reference/share/RDPTools/Xander_assembler/gene_resource/%s/ref_aligned.faa" % gene
+    if not os.path.exists(faa):
+        pytest.skip("the reference tree is not present")
+    for k in (10, 15):
+        rows, text = ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_char_p()
+        n = host.hd_model_kmers(faa.encode(), k, ctypes.byref(rows), ctypes.byref(text))
+        r = np.ctypeslib.as_array(rows, (max(n, 1), 3))[:n].copy()
+        t = ctypes.string_at(text, n * k).decode()
+        host.hd_free(rows)
+        host.hd_free(text)
+        got = {}
+        for i in range(n):
+            got.setdefault(t[i * k:(i + 1) * k].upper(), int(r[i, 2]))
+        assert n > 10000 and got == ST.model_kmers(faa, k)

@@ -66,3 +66,24 @@ def test_findstart_oracle_equals_the_reference_digests(tmp_path, k_size, with_co
     golden = json.load(open(os.path.join(datasets.GOLDEN_DIR, "findstart_golden.json")))
     lines = ST.find_seeds(ref, binf, k_size, contigs if with_contigs else None)
     assert T.digest(lines) == golden["k%d_contigs%d" % (k_size, int(with_contigs))]
+
+
+GENE_DIR = "/root/reference/share/RDPTools/Xander_assembler/gene_resource"
+GENES = ["nifH", "rplB", "nirK", "nirS", "nosZ", "nosZ_a2", "norB_cNor", "norB_qNor", "amoA_AOA", "amoA_AOB"]
+
+
+@pytest.mark.parametrize("gene", GENES)
+def test_findstart_oracle_equals_the_reference_on_its_own_gene_alignments(tmp_path, gene):
+    """the reference's own aligned gene families (only in this container: the tree is absent on the GPU box) against the
+    reference's in-tree reads (tests/golden/xander.bin = its test_reads.fa): the UNMODIFIED `findstart`, run live, and the
+    oracle give the same seed lines (the reference shuffles them: compared sorted)"""
+    import subprocess
+    faa = os.path.join(GENE_DIR, gene, "ref_aligned.faa")
+    if not os.path.exists(faa) or not O.have_ref():
+        pytest.skip("the reference tree / oracle/_ref is not present")
+    binf = os.path.join(datasets.GOLDEN_DIR, "xander.bin")
+    for k_size in (45, 30):
+        r = subprocess.run([O.REF_BIN, "findstart", faa, binf, str(k_size), "2"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1000:]
+        want = sorted(l for l in r.stdout.splitlines() if l)
+        assert ST.find_seeds(faa, binf, k_size) == want
