@@ -204,3 +204,31 @@ def test_node_pass_reproduces_the_records(logic, read_lib, ds, k, m, mercy):
     if not mercy:
         stream, meta, totals = run_edges(logic, rd, k, m, None, fused=5)     # multiplicities straight from the stage-1 counts
         assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
+
+
+@pytest.mark.parametrize("seed", range(52))
+def test_product_logic_on_random_inputs(logic, tmp_path, seed):
+    """the seeded random read sets of tests/test_oracle_fuzz.py (ragged lengths, repeats, palindromes, k = 9 ... 127 around
+    every word boundary, min-count 1..3, mercy) through the product's item / node-pass / emission logic, against the oracle
+    (which that file pins on the reference binary run live)"""
+    import test_oracle_fuzz as F
+    prefix, k, m, mercy, fa = F.make_case(seed, str(tmp_path))
+    rd = O.load_read_lib(prefix)
+    exp_solid = None
+    if m > 1:
+        exp_solid, exp_ec, cands = O.stage1(rd, k, m, mercy)
+        got_solid = np.zeros(len(exp_solid) + 8, dtype=np.uint8)
+        got_ec = np.zeros(65536, dtype=np.int64)
+        assert lib_stage1_edges(logic, rd, k, m, got_solid, got_ec) == 0                 # canonical (k+1)-mer counting
+        assert np.array_equal(got_ec, exp_ec) and np.array_equal(got_solid[:len(exp_solid)], exp_solid)
+        if mercy:
+            got = run_logic(logic, rd, k, m, True)                                         # the reference's own stage-1 items + mercy
+            assert np.array_equal(got["cands"], cands)
+            O.mercy(rd, k, exp_solid, cands)
+            assert np.array_equal(got["is_solid"][:len(exp_solid)], exp_solid)
+    exp = O.stage2(rd, k, m, exp_solid)
+    stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=4)                  # node pass (the product's stage 2)
+    assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
+    if not mercy:
+        stream, meta, totals = run_edges(logic, rd, k, m, None, fused=5)                   # multiplicities from the stage-1 counts
+        assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
