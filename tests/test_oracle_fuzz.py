@@ -89,3 +89,26 @@ def test_oracle_equals_the_reference_on_random_inputs(seed, tmp_path):
                                 if x.startswith("ref.mercy_cand.")] or [np.empty(0, "<u8")])
         mine = O.stage1(rd, k, m, True)[2]
         assert np.array_equal(np.sort(cands), np.sort(mine))
+
+
+@pytest.mark.parametrize("seed", range(0, 52, 2))
+def test_sdbg_oracle_equals_the_reference_loader_on_random_graphs(seed, tmp_path):
+    """oracle/sdbg_oracle.py (numpy restatement of SuccinctDBG::LoadFromMultiFile + the rank / select builds) against dumps of
+    the reference's own members (`megagta_ref sdbgdump`) for the graphs of the random read sets above, both multiplicity modes"""
+    from oracle import sdbg_oracle as SO
+    if not O.have_ref() or "sdbgdump" not in open(O.REF_BIN, "rb").read().decode("latin1"):
+        pytest.skip("oracle/_ref/megagta_ref with sdbgdump not built")
+    d = str(tmp_path)
+    prefix, k, m, mercy, fa = make_case(seed, d)
+    out = os.path.join(d, "ref")
+    try:
+        O.run_ref_buildgraph(prefix, out, k, m, threads=2, need_mercy=mercy and not fa, assist_seq=fa)
+    except subprocess.CalledProcessError:
+        pytest.skip("the reference itself fails on this input (no solid edge)")
+    hdr, stream, meta = sdbg_io.canonical(out)
+    for need_mult in (1, 0):
+        ref = SO.ref_dump(O.REF_BIN, out, need_mult, os.path.join(d, "dump"))
+        ref.pop("_load_seconds", None)
+        want = SO.build(stream, np.asarray(meta), k, bool(need_mult))
+        bad = [sec for sec in ref if want.get(sec) != ref[sec]]
+        assert not bad, (bad, k, m)
