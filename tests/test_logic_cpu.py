@@ -162,7 +162,7 @@ def test_device_mercy_scan_on_cpu_matches_oracle(logic, read_lib, ds, k, m):
     assert np.array_equal(got, exp)
 
 
-@pytest.mark.parametrize("ds,k,m,mercy", EDGE_CASES)
+@pytest.mark.parametrize("ds,k,m,mercy", [c for c in EDGE_CASES if c[0] != "smoke" or c[1:] in ((31, 2, False), (31, 2, True), (63, 1, False))])
 def test_node_filter_drops_only_items_the_group_logic_drops(logic, read_lib, ds, k, m, mercy):
     """Design check for the next step: with a k-mer node table (which k-mers a solid edge enters /
     leaves) the $-items that output_() would drop anyway are never generated; the records must not change."""
