@@ -119,6 +119,11 @@ def load():
         lib.mgta_stage2_into_sdbg.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.mgta_pack_reads.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]
         lib.mgta_tools_last_error.restype = ctypes.c_char_p
+        lib.mgta_find_seeds.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                        ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                        ctypes.POINTER(ctypes.c_uint64)]
+        lib.mgta_sdbg_sink.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        lib.mgta_words_per_key.argtypes = [ctypes.c_int, ctypes.c_int]
         _lib = lib
     return _lib
 

@@ -63,3 +63,12 @@ def test_ctypes_structs_have_the_layout_of_the_header(tmp_path):
         for field, _ in cls._fields_:
             assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, (name, field)
     assert cabi.COLL_ALL_REDUCE_SUM_U64 == 4 and cabi.SDBG_TIP_MAJOR == 23 and cabi.SDBG_TIP_SEQ == 8
+
+
+def test_every_entry_point_with_arguments_has_its_argument_types_declared():
+    """without argtypes ctypes passes Python ints as C int: a 64-bit count or pointer would be truncated silently"""
+    lib = cabi.load()
+    no_args = {"mgta_abi_version", "mgta_tools_last_error"}
+    missing = [n for n in cabi.EXPORTS if n not in no_args and getattr(lib, n).argtypes is None]
+    assert not missing, missing
+    assert lib.mgta_words_per_key(1, 31) == 3 and lib.mgta_words_per_key(2, 31) == 3 and lib.mgta_words_per_key(2, 99) == 7
