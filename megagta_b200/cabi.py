@@ -240,17 +240,26 @@ class Context:
         nbytes_total = [0]
         meta = np.zeros((NUM_BUCKETS, 3), dtype=np.int64)
 
+        failed = []
+
         def sink(user, b0, b1, ptr, nbytes, mptr):
-            if nbytes and collect is True:
-                for o in range(0, nbytes, 1 << 30):          # ctypes.string_at takes a C int size: slices of 1 GiB
-                    parts.append(ctypes.string_at(ptr + o, min(1 << 30, nbytes - o)))
-            nbytes_total[0] += nbytes
-            meta[b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
-            return 0
+            try:
+                if nbytes and collect is True:
+                    for o in range(0, nbytes, 1 << 30):      # ctypes.string_at takes a C int size: slices of 1 GiB
+                        parts.append(ctypes.string_at(ptr + o, min(1 << 30, nbytes - o)))
+                nbytes_total[0] += nbytes
+                meta[b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
+                return 0
+            except BaseException as e:                       # ctypes would print and swallow it: abort the stage instead
+                failed.append(e)
+                return -1
 
         cb = SINK(sink) if collect else ctypes.cast(None, SINK)
         totals = np.zeros(10, dtype=np.int64)
-        self._check(self.lib.mgta_stage2(self.h, cb, None, _p(totals)), "mgta_stage2")
+        rc = self.lib.mgta_stage2(self.h, cb, None, _p(totals))
+        if failed:
+            raise failed[0]
+        self._check(rc, "mgta_stage2")
         return (b"".join(parts) if collect is True else nbytes_total[0]), meta, totals
 
     # ---- sharded build (world > 1): the library walks the protocol, the caller runs the collectives it asks for
@@ -260,12 +269,16 @@ class Context:
         sh = self._sh
 
         def sink(user, b0, b1, ptr, nbytes, mptr):
-            if nbytes and collect is True:
-                for o in range(0, nbytes, 1 << 30):          # ctypes.string_at takes a C int size: slices of 1 GiB
-                    sh["parts"].append(ctypes.string_at(ptr + o, min(1 << 30, nbytes - o)))
-            sh["nbytes"] += nbytes
-            sh["meta"][b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
-            return 0
+            try:
+                if nbytes and collect is True:
+                    for o in range(0, nbytes, 1 << 30):      # ctypes.string_at takes a C int size: slices of 1 GiB
+                        sh["parts"].append(ctypes.string_at(ptr + o, min(1 << 30, nbytes - o)))
+                sh["nbytes"] += nbytes
+                sh["meta"][b0:b1] = np.ctypeslib.as_array(mptr, shape=((b1 - b0) * 3,)).reshape(b1 - b0, 3)
+                return 0
+            except BaseException as e:                       # ctypes would print and swallow it: abort the stage instead
+                sh["failed"] = e
+                return -1
 
         sh["cb"] = SINK(sink) if (collect and stage == 2) else ctypes.cast(None, SINK)      # kept alive until the result is read
         self._check(self.lib.mgta_sharded_begin(self.h, stage, sh["cb"], None), "mgta_sharded_begin")
@@ -273,7 +286,10 @@ class Context:
     def sharded_step(self):
         """-> Collective to run among the shards on this context's stream, or None when the stage has finished"""
         c = Collective()
-        self._check(self.lib.mgta_sharded_step(self.h, ctypes.byref(c)), "mgta_sharded_step")
+        rc = self.lib.mgta_sharded_step(self.h, ctypes.byref(c))
+        if self._sh.get("failed") is not None:
+            raise self._sh["failed"]
+        self._check(rc, "mgta_sharded_step")
         return None if c.op == COLL_NONE else c
 
     def sharded_result(self):
