@@ -5,7 +5,8 @@
 // (oracle/Makefile, target level2): OptionsDescription parses the command line, s1_read_input_prepare
 // (cx1_read2sdbg_s1.cpp:96-175) loads the read library and the --assist_seq file into its SequencePackage, and
 // SdbgWriter (sdbg_multi_io.h:34-199) writes <P>.sdbg.0 and <P>.sdbg_info.  No reference source is changed or copied:
-// the package's two arrays are public members, and the records are replayed through SdbgWriter::write.
+// the package's two arrays are public members, and the records are replayed through SdbgWriter::write -- or, built with
+// -DMGTA_HAVE_APPEND_RAW against a tree that carries integration/sdbg_writer_append_raw.patch, appended with one fwrite per delivery.
 // (One GPU; for several GPUs run the loop of megagta_b200/csrc/host/buildgraph_b200.cpp gpu_thread() per device.)
 //
 //   megagta_level2 buildgraph -k 31 -m 2 --host_mem 8e9 --num_cpu_threads 4 --read_lib_file X --output_prefix P
@@ -104,24 +105,59 @@ static int build_graph_b200(int argc, char **argv) {
         writer.init_files();
         Level2Sink sink = {&writer, (2 * opt.kmer_k + 31) / 32, 0};
         int64_t totals[10];
-        if (mgta_stage2(ctx, level2_replay_sink, &sink, totals) != 0) { xerr_and_exit("%s\n", mgta_last_error(ctx)); }
+        if (mgta_stage2(ctx, LEVEL2_SINK, &sink, totals) != 0) { xerr_and_exit("%s\n", mgta_last_error(ctx)); }
         xlog("Number of $ A C G T A- C- G- T-:\n");                       // the reference's closing log (s2.cpp:905-915)
         xlog("");
-        for (int i = 0; i < 9; ++i) xlog_ext("%lld ", (long long)writer.num_w(i));
+        for (int i = 0; i < 9; ++i) xlog_ext("%lld ", (long long)totals[i]);
         xlog_ext("\n");
         xlog("Total number of edges: %lld\n", (long long)writer.num_edges());
         xlog("Total number of ONEs: %lld\n", (long long)writer.num_last1());
         xlog("Total number of $v edges: %lld\n", (long long)writer.num_tips());
+#ifndef MGTA_HAVE_APPEND_RAW                                              // (append_raw does not count W: the totals are the library's)
         for (int i = 0; i < 9; ++i)
             if (writer.num_w(i) != totals[i]) { xerr_and_exit("internal: W totals of the library and of the writer differ\n"); }
+#endif
     }                                                                     // ~SdbgWriter closes the files and writes sdbg_info
     mgta_ctx_destroy(ctx);
     delete g;
     return 0;
 }
 
+// replay <stream file> <meta file: int64[65536][3]> <k> <out prefix> <buckets per delivery>: a recorded bucket-ordered record
+// stream handed to the sink in deliveries (no GPU involved) -- how the tests check the sink and the reference's writer
+static int replay(int argc, char **argv) {
+    if (argc < 6) { fprintf(stderr, "usage: replay <stream> <meta> <k> <out_prefix> <buckets_per_delivery>\n"); return 1; }
+    const int k = atoi(argv[3]), per = atoi(argv[5]) > 0 ? atoi(argv[5]) : 65536, wpt = (2 * k + 31) / 32;
+    std::vector<unsigned char> stream;
+    std::vector<int64_t> meta(65536 * 3);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f) return 1;
+    fseek(f, 0, SEEK_END); stream.resize(ftell(f)); fseek(f, 0, SEEK_SET);
+    if (!stream.empty() && fread(&stream[0], 1, stream.size(), f) != stream.size()) return 1;
+    fclose(f);
+    f = fopen(argv[2], "rb");
+    if (!f || fread(&meta[0], 8, meta.size(), f) != meta.size()) return 1;
+    fclose(f);
+    SdbgWriter writer;
+    writer.set_num_threads(1); writer.set_file_prefix(argv[4]); writer.set_kmer_size(k); writer.set_num_buckets(65536);
+    writer.init_files();
+    Level2Sink sink = {&writer, wpt, 0};
+    size_t at = 0;
+    for (int b0 = 0; b0 < 65536; b0 += per) {
+        const int b1 = b0 + per < 65536 ? b0 + per : 65536;
+        size_t bytes = 0;
+        for (int b = b0; b < b1; ++b) bytes += meta[b * 3] * 2 + meta[b * 3 + 2] * 2 + meta[b * 3 + 1] * 4 * wpt;
+        if (at + bytes > stream.size()) bytes = stream.size() - at;      // a table that claims more than the stream holds
+        const int rc = LEVEL2_SINK(&sink, b0, b1, stream.empty() ? NULL : &stream[at], bytes, &meta[b0 * 3]);
+        if (rc) { fprintf(stderr, "sink returned %d\n", rc); return 3; }
+        at += bytes;
+    }
+    return at == stream.size() ? 0 : 4;
+}
+
 int main(int argc, char **argv) {
     if (argc >= 2 && strcmp(argv[1], "buildgraph") == 0) return build_graph_b200(argc - 1, argv + 1);
+    if (argc >= 2 && strcmp(argv[1], "replay") == 0) return replay(argc - 1, argv + 1);
     fprintf(stderr, "usage: %s buildgraph [options of `megagta buildgraph`]\n", argv[0]);
     return 1;
 }

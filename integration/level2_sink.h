@@ -41,3 +41,22 @@ inline int level2_replay_sink(void *user, int32_t bucket_begin, int32_t bucket_e
     }
     return p == end ? 0 : -2;                                            // the table must add up to the bytes delivered
 }
+
+#ifdef MGTA_HAVE_APPEND_RAW
+// The fast binding, for a reference tree that carries integration/sdbg_writer_append_raw.patch: one fwrite per delivery.
+inline int level2_raw_sink(void *user, int32_t bucket_begin, int32_t bucket_end, const void *bytes, uint64_t n_bytes,
+                           const int64_t *meta) {
+    Level2Sink *s = static_cast<Level2Sink *>(user);
+    uint64_t expect = 0;
+    for (int32_t b = bucket_begin; b < bucket_end; ++b) {
+        const int64_t *m = meta + (size_t)(b - bucket_begin) * 3;
+        expect += (uint64_t)m[0] * 2 + (uint64_t)m[2] * 2 + (uint64_t)m[1] * 4 * (uint64_t)s->words_per_tip_label;
+    }
+    if (expect != n_bytes) return -2;                                    // the table must add up to the bytes delivered
+    s->writer->append_raw(s->file_id, bucket_begin, bucket_end, bytes, n_bytes, meta);
+    return 0;
+}
+#define LEVEL2_SINK level2_raw_sink
+#else
+#define LEVEL2_SINK level2_replay_sink
+#endif

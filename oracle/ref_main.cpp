@@ -9,7 +9,6 @@
 #include "succinct_dbg.h"
 #undef private
 #include "cx1_read2sdbg.h"
-#include "level2_sink.h"           // integration/: the Level-2 sink, replayed here on the CPU (replaysink)
 int build_lib(int argc, char **argv);
 int build_graph(int argc, char **argv);
 int main_assemble(int argc, char **argv);
@@ -105,42 +104,8 @@ static int reads_dump(int argc, char **argv) {
     return 0;
 }
 
-// replaysink <stream file> <meta file: int64[65536][3]> <k> <out prefix> <buckets per delivery>: a bucket-ordered record
-// stream handed to integration/level2_sink.h in deliveries, i.e. replayed through the reference's own SdbgWriter::write
-static int replay_sink(int argc, char **argv) {
-    if (argc < 6) { fprintf(stderr, "usage: replaysink <stream> <meta> <k> <out_prefix> <buckets_per_delivery>\n"); return 1; }
-    const int k = atoi(argv[3]), per = atoi(argv[5]) > 0 ? atoi(argv[5]) : 65536, wpt = (2 * k + 31) / 32;
-    std::vector<unsigned char> stream;
-    std::vector<int64_t> meta(65536 * 3);
-    {
-        FILE *f = fopen(argv[1], "rb");
-        if (!f) return 1;
-        fseek(f, 0, SEEK_END); stream.resize(ftell(f)); fseek(f, 0, SEEK_SET);
-        if (!stream.empty() && fread(&stream[0], 1, stream.size(), f) != stream.size()) return 1;
-        fclose(f);
-        f = fopen(argv[2], "rb");
-        if (!f || fread(&meta[0], 8, meta.size(), f) != meta.size()) return 1;
-        fclose(f);
-    }
-    SdbgWriter writer;
-    writer.set_num_threads(1); writer.set_file_prefix(argv[4]); writer.set_kmer_size(k); writer.set_num_buckets(65536);
-    writer.init_files();
-    Level2Sink sink = {&writer, wpt, 0};
-    size_t at = 0;
-    for (int b0 = 0; b0 < 65536; b0 += per) {
-        const int b1 = b0 + per < 65536 ? b0 + per : 65536;
-        size_t bytes = 0;
-        for (int b = b0; b < b1; ++b) bytes += meta[b * 3] * 2 + meta[b * 3 + 2] * 2 + meta[b * 3 + 1] * 4 * wpt;
-        if (at + bytes > stream.size()) return 2;
-        const int rc = level2_replay_sink(&sink, b0, b1, stream.empty() ? NULL : &stream[at], bytes, &meta[b0 * 3]);
-        if (rc) { fprintf(stderr, "sink returned %d\n", rc); return 3; }
-        at += bytes;
-    }
-    return at == stream.size() ? 0 : 4;
-}
 
 int main(int argc, char **argv) {
-    if (argc >= 2 && strcmp(argv[1], "replaysink") == 0) return replay_sink(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "readsdump") == 0) return reads_dump(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "sdbgdump") == 0) return sdbg_dump(argc - 1, argv + 1);
     if (argc >= 2 && strcmp(argv[1], "buildlib") == 0) return build_lib(argc - 1, argv + 1);

@@ -16,14 +16,15 @@ LEVEL2 = os.path.join(ROOT, "oracle", "_ref", "megagta_level2")
 
 
 @pytest.mark.skipif(os.environ.get("MGTA_TEST_LEVEL2") != "1", reason="opt-in: MGTA_TEST_LEVEL2=1 (not yet run on a GPU)")
-@pytest.mark.parametrize("case", ["smoke_k31_m2", "smoke_k61_m2", "adversarial_k27_m3", "xander_k29_m1"])
-def test_level2_writes_the_reference_files(case, golden, read_lib, tmp_path):
-    if not os.path.exists(LEVEL2):
-        pytest.skip("oracle/_ref/megagta_level2 not built")
+@pytest.mark.parametrize("variant", ["", "_raw"])      # SdbgWriter::write per record / append_raw per delivery (patched tree)
+@pytest.mark.parametrize("case", ["smoke_k31_m2", "adversarial_k27_m3"])
+def test_level2_writes_the_reference_files(case, variant, golden, read_lib, tmp_path):
+    if not os.path.exists(LEVEL2 + variant):
+        pytest.skip("oracle/_ref/megagta_level2%s not built" % variant)
     g = golden["cases"][case]
     prefix, _ = read_lib(g["dataset"])
     out = str(tmp_path / "g")
-    r = subprocess.run([LEVEL2, "buildgraph", "-k", str(g["k"]), "-m", str(g["m"]), "--host_mem", "4e9", "--num_cpu_threads", "4",
+    r = subprocess.run([LEVEL2 + variant, "buildgraph", "-k", str(g["k"]), "-m", str(g["m"]), "--host_mem", "4e9", "--num_cpu_threads", "4",
                         "--num_output_threads", "1", "--read_lib_file", prefix, "--output_prefix", out], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     hdr, stream, meta = sdbg_io.canonical(out)
