@@ -9,7 +9,8 @@
  * Parity status: PINNED.  tests/test_oracle.py checks this restatement against golden hashes that
  * were produced by the unmodified reference binary (oracle/_ref/megagta_ref, built by
  * oracle/Makefile from /root/reference/src) with tests/golden/make_golden.py; SURVEY.md Appendix C
- * lists the same hashes for the shared cases.
+ * lists the same hashes for the shared cases; tests/test_oracle_fuzz.py compares it with the reference
+ * binary run live on 52 seeded random read sets (k = 9 ... 127, min-count 1 ... 3, mercy, assist reads).
  *
  * It deliberately does NOT follow the reference's schedule (lv1 passes, int32 delta offsets,
  * kt_dfor work stealing: /root/reference/src/cx1.h:443-623) -- only its observable results:
