@@ -64,8 +64,6 @@ def test_oracle_equals_the_reference_on_random_inputs(seed, tmp_path):
         pytest.skip("oracle/_ref/megagta_ref not built")
     d = str(tmp_path)
     prefix, k, m, mercy, fa = make_case(seed, d)
-    if mercy and fa:
-        mercy = False                                               # one extension at a time
     out = os.path.join(d, "ref")
     try:
         log = O.run_ref_buildgraph(prefix, out, k, m, threads=2, need_mercy=mercy, assist_seq=fa)
@@ -87,7 +85,7 @@ def test_oracle_equals_the_reference_on_random_inputs(seed, tmp_path):
         assert mm and int(mm.group(1)) == int(res["num_mercy"])
         cands = np.concatenate([np.fromfile(os.path.join(d, x), dtype="<u8") for x in sorted(os.listdir(d))
                                 if x.startswith("ref.mercy_cand.")] or [np.empty(0, "<u8")])
-        mine = O.stage1(rd, k, m, True)[2]
+        mine = O.stage1(rd, k, m, True, n_short)[2]
         assert np.array_equal(np.sort(cands), np.sort(mine))
 
 
@@ -102,7 +100,7 @@ def test_sdbg_oracle_equals_the_reference_loader_on_random_graphs(seed, tmp_path
     prefix, k, m, mercy, fa = make_case(seed, d)
     out = os.path.join(d, "ref")
     try:
-        O.run_ref_buildgraph(prefix, out, k, m, threads=2, need_mercy=mercy and not fa, assist_seq=fa)
+        O.run_ref_buildgraph(prefix, out, k, m, threads=2, need_mercy=mercy, assist_seq=fa)
     except subprocess.CalledProcessError:
         pytest.skip("the reference itself fails on this input (no solid edge)")
     hdr, stream, meta = sdbg_io.canonical(out)
