@@ -30,9 +30,9 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_logic(lib, rd, k, m, mercy):
-    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
-    is_solid = np.zeros(O.solid_bytes(rd, k) + 8, dtype=np.uint8)
+def run_logic(lib, rd, k, m, mercy, n_short=None):
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"] if n_short is None else n_short)
+    is_solid = np.zeros(O.solid_bytes(rd, k, n_short) + 8, dtype=np.uint8)
     ec = np.zeros(65536, dtype=np.int64)
     h1 = np.zeros(65536, dtype=np.int64)
     cands = np.empty(0, dtype=np.uint64)
@@ -45,7 +45,7 @@ def run_logic(lib, rd, k, m, mercy):
             ctypes.memmove(_p(cands), cp, cn.value * 8)
         lib.logic_free(cp)
         if mercy:
-            O.mercy(rd, k, is_solid, cands)
+            O.mercy(rd, k, is_solid, cands, n_short)
     sp, sn = ctypes.c_void_p(), ctypes.c_int64()
     meta = np.zeros((65536, 3), dtype=np.int64)
     totals = np.zeros(10, dtype=np.int64)
@@ -86,8 +86,8 @@ def test_device_logic_on_cpu_matches_oracle(logic, read_lib, ds, k, m, mercy):
 
 
 # ---- edge-centric path (v2): the canonical-(k+1)-mer multiset gives stage 1, and {(edge, solid occurrences)} gives stage 2
-def run_edges(lib, rd, k, m, is_solid=None, fused=False):
-    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
+def run_edges(lib, rd, k, m, is_solid=None, fused=False, n_short=None):
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"] if n_short is None else n_short)
     sp, sn = ctypes.c_void_p(), ctypes.c_int64()
     meta = np.zeros((65536, 3), dtype=np.int64)
     totals = np.zeros(10, dtype=np.int64)
@@ -135,8 +135,8 @@ def test_edge_centric_logic_matches_oracle(logic, read_lib, ds, k, m, mercy):
         assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
 
 
-def lib_stage1_edges(lib, rd, k, m, solid, ec):
-    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"])
+def lib_stage1_edges(lib, rd, k, m, solid, ec, n_short=None):
+    n, ns = ctypes.c_int64(rd["n_reads"]), ctypes.c_int64(rd["n_reads"] if n_short is None else n_short)
     return lib.logic_stage1_edges(_p(rd["seq"]), _p(rd["start"]), n, ns, rd["max_len"], k, m, _p(solid), _p(ec))
 
 
@@ -209,26 +209,28 @@ def test_node_pass_reproduces_the_records(logic, read_lib, ds, k, m, mercy):
 @pytest.mark.parametrize("seed", range(52))
 def test_product_logic_on_random_inputs(logic, tmp_path, seed):
     """the seeded random read sets of tests/test_oracle_fuzz.py (ragged lengths, repeats, palindromes, k = 9 ... 127 around
-    every word boundary, min-count 1..3, mercy) through the product's item / node-pass / emission logic, against the oracle
-    (which that file pins on the reference binary run live)"""
+    every word boundary, min-count 1..3, mercy, assist reads) through the product's item / node-pass / emission logic, against
+    the oracle (which that file pins on the reference binary run live)"""
     import test_oracle_fuzz as F
     prefix, k, m, mercy, fa = F.make_case(seed, str(tmp_path))
-    rd = O.load_read_lib(prefix)
+    rd, ns = O.load_read_lib(prefix), None
+    if fa:
+        rd, ns = O.with_assist(rd, fa)
     exp_solid = None
     if m > 1:
-        exp_solid, exp_ec, cands = O.stage1(rd, k, m, mercy)
+        exp_solid, exp_ec, cands = O.stage1(rd, k, m, mercy, ns)
         got_solid = np.zeros(len(exp_solid) + 8, dtype=np.uint8)
         got_ec = np.zeros(65536, dtype=np.int64)
-        assert lib_stage1_edges(logic, rd, k, m, got_solid, got_ec) == 0                 # canonical (k+1)-mer counting
+        assert lib_stage1_edges(logic, rd, k, m, got_solid, got_ec, ns) == 0             # canonical (k+1)-mer counting
         assert np.array_equal(got_ec, exp_ec) and np.array_equal(got_solid[:len(exp_solid)], exp_solid)
         if mercy:
-            got = run_logic(logic, rd, k, m, True)                                         # the reference's own stage-1 items + mercy
+            got = run_logic(logic, rd, k, m, True, ns)                                     # the reference's own stage-1 items + mercy
             assert np.array_equal(got["cands"], cands)
-            O.mercy(rd, k, exp_solid, cands)
+            O.mercy(rd, k, exp_solid, cands, ns)
             assert np.array_equal(got["is_solid"][:len(exp_solid)], exp_solid)
-    exp = O.stage2(rd, k, m, exp_solid)
-    stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=4)                  # node pass (the product's stage 2)
+    exp = O.stage2(rd, k, m, exp_solid, ns)
+    stream, meta, totals = run_edges(logic, rd, k, m, exp_solid, fused=4, n_short=ns)      # node pass (the product's stage 2)
     assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
     if not mercy:
-        stream, meta, totals = run_edges(logic, rd, k, m, None, fused=5)                   # multiplicities from the stage-1 counts
+        stream, meta, totals = run_edges(logic, rd, k, m, None, fused=5, n_short=ns)       # multiplicities from the stage-1 counts
         assert stream == exp[0] and np.array_equal(meta, exp[1]) and np.array_equal(totals, exp[2])
